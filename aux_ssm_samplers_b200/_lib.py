@@ -1,0 +1,126 @@
+"""ctypes binding of libauxssm.so (the C ABI declared in include/auxssm.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+PyTorch is used only for device memory, streams and (elsewhere) torch.distributed.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libauxssm.so")
+
+AUXSSM_MAX_DIM = 64
+FLAG_H_IDENTITY = 1
+LOGPDF_PRIOR, LOGPDF_LOGLIK, LOGPDF_MINUS_ELL, LOGPDF_POSTERIOR = 1, 2, 4, 7
+
+
+class AuxssmError(RuntimeError):
+    pass
+
+
+class Stride(ctypes.Structure):
+    _fields_ = [("chain", ctypes.c_int64), ("batch", ctypes.c_int64), ("time", ctypes.c_int64)]
+
+
+class LgssmDesc(ctypes.Structure):
+    _fields_ = [
+        ("T", ctypes.c_int32), ("dx", ctypes.c_int32), ("dy", ctypes.c_int32),
+        ("n_chains", ctypes.c_int32), ("n_batch", ctypes.c_int32),
+        ("parallel", ctypes.c_int32), ("time_chunks", ctypes.c_int32), ("flags", ctypes.c_uint32),
+        ("ys", Stride), ("m0", Stride), ("P0", Stride), ("Fs", Stride), ("Qs", Stride), ("bs", Stride),
+        ("Hs", Stride), ("Rs", Stride), ("cs", Stride), ("ms", Stride), ("Ps", Stride),
+        ("eps", Stride), ("xs", Stride),
+    ]
+
+
+_P = ctypes.c_void_p
+_I32, _I64, _U32, _SZ = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_size_t
+_DESC = ctypes.POINTER(LgssmDesc)
+
+# name -> (restype, argtypes); `{s}` expands to f32 / f64
+_SIGNATURES = {
+    "auxssm_last_error": (ctypes.c_char_p, []),
+    "auxssm_version": (_I32, []),
+    "auxssm_kalman_filter_scratch_bytes": (_SZ, [_DESC, _I32]),
+    "auxssm_kalman_filter_{s}": (_I32, [_P, _DESC] + [_P] * 12 + [_P, _SZ]),
+    "auxssm_kalman_sample_scratch_bytes": (_SZ, [_DESC, _I32]),
+    "auxssm_kalman_sample_{s}": (_I32, [_P, _DESC] + [_P] * 7 + [_P, _SZ]),
+    "auxssm_lgssm_logpdf_scratch_bytes": (_SZ, [_DESC, _I32]),
+    "auxssm_lgssm_logpdf_{s}": (_I32, [_P, _DESC, _U32] + [_P] * 12 + [_P, _SZ]),
+    "auxssm_auxiliary_draw_{s}": (_I32, [_P, _I64, _I64, _P, _P, _P, _I32, _P]),
+    "auxssm_kalman_mh_{s}": (_I32, [_P, _I64, _I64, _P, _I32] + [_P] * 10),
+    "auxssm_sv_obs_factory_{s}": (_I32, [_P, _I32, _I64, _I64, _I32, _P, _I64, _P, _P, _P, _I32, _P, _P]),
+    "auxssm_sv_log_potential_{s}": (_I32, [_P, _I64, _I64, _P, _I64, _P, _P, _I32]),
+}
+
+
+def exported_symbols():
+    """Every symbol include/auxssm.h declares (used by the CPU-side ABI test)."""
+    out = []
+    for name in _SIGNATURES:
+        if "{s}" in name:
+            out += [name.format(s="f32"), name.format(s="f64")]
+        else:
+            out.append(name)
+    return out
+
+
+_lib = None
+
+
+def lib():
+    """Load libauxssm.so (once).  Raises AuxssmError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AuxssmError(
+            "libauxssm.so not found at %s -- build it with `python -m aux_ssm_samplers_b200.build` "
+            "(or __graft_entry__.build()); there is no CPU fallback." % LIB_PATH)
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        for s in (("f32", "f64") if "{s}" in name else ("",)):
+            fn = getattr(handle, name.format(s=s))
+            fn.restype = res
+            fn.argtypes = args
+    _lib = handle
+    return _lib
+
+
+def suffix(dtype):
+    if dtype == torch.float32:
+        return "f32"
+    if dtype == torch.float64:
+        return "f64"
+    raise AuxssmError("libauxssm supports float32 and float64 only, got %s" % dtype)
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().auxssm_last_error().decode("utf-8", "replace")
+        raise AuxssmError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def require_cuda(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise AuxssmError("libauxssm operates on CUDA tensors only (got a %s tensor); there is no CPU path"
+                              % t.device)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise AuxssmError("all tensors must live on the same CUDA device")
+    return dev

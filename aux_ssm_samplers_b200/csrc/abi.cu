@@ -1,0 +1,72 @@
+// libauxssm: error channel, descriptor validation and launch policy shared by all entry points.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace auxssm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int device_sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  return n;
+}
+
+size_t device_max_smem() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 48 * 1024;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || n <= 0)
+    return 48 * 1024;
+  return (size_t)n;
+}
+
+int resolve_time_chunks(const auxssm_lgssm_desc* d) {
+  if (!d->parallel || d->T < 3) return 1;
+  const int n_elem = d->T - 1;
+  if (d->time_chunks > 0) return d->time_chunks < n_elem ? d->time_chunks : n_elem;
+  // Automatic policy.  Parallel-in-time costs ~4x the flops of the sequential recursion, so it
+  // only pays while independent units (chains x inner batch) leave SMs idle.  Target ~4 CTAs per
+  // SM; never more chunks than ~sqrt(6 T) (the cross-chunk prefix pass is sequential).
+  const long units = (long)d->n_chains * d->n_batch;
+  const long target = 4L * device_sm_count();
+  if (units >= target) return 1;
+  long want = (target + units - 1) / units;
+  long cap = 1;
+  while (cap * cap < 6L * n_elem) ++cap;
+  if (want > cap) want = cap;
+  if (want > n_elem) want = n_elem;
+  return want < 1 ? 1 : (int)want;
+}
+
+int check_desc(const auxssm_lgssm_desc* d, const char* who) {
+  if (d == nullptr) { set_error("%s: null descriptor", who); return AUXSSM_ERR_INVALID; }
+  if (d->T < 1 || d->dx < 1 || d->dy < 1 || d->n_chains < 1 || d->n_batch < 1) {
+    set_error("%s: T, dx, dy, n_chains, n_batch must be >= 1 (got %d %d %d %d %d)", who, d->T, d->dx, d->dy,
+              d->n_chains, d->n_batch);
+    return AUXSSM_ERR_INVALID;
+  }
+  if (d->dx > AUXSSM_MAX_DIM || d->dy > AUXSSM_MAX_DIM) {
+    set_error("%s: dx=%d / dy=%d exceed AUXSSM_MAX_DIM=%d", who, d->dx, d->dy, AUXSSM_MAX_DIM);
+    return AUXSSM_ERR_UNSUPPORTED;
+  }
+  if ((d->flags & AUXSSM_FLAG_H_IDENTITY) && d->dx != d->dy) {
+    set_error("%s: AUXSSM_FLAG_H_IDENTITY requires dy == dx", who);
+    return AUXSSM_ERR_INVALID;
+  }
+  if (d->time_chunks < 0) { set_error("%s: time_chunks must be >= 0", who); return AUXSSM_ERR_INVALID; }
+  return AUXSSM_OK;
+}
+
+}  // namespace auxssm
+
+extern "C" __attribute__((visibility("default"))) const char* auxssm_last_error(void) { return auxssm::g_err; }
+extern "C" __attribute__((visibility("default"))) int32_t auxssm_version(void) { return AUXSSM_VERSION; }

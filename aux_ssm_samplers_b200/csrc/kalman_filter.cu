@@ -1,0 +1,601 @@
+// Kalman filtering for (batches of) linear-Gaussian state-space models.
+//
+// Replaces aux_samplers/_primitives/kalman/filtering.py of the reference:
+//   filtering:18-46, _sequential_filtering:66-79, sequential_update:84-130,
+//   sequential_predict:135-139, _parallel_filtering:49-63, _filtering_init_one:197-250,
+//   _filtering_op_impl:164-183.
+//
+// Layout on the GPU: one CTA per (chain, inner-batch unit, time chunk); every d x d operand
+// lives in shared memory (see smem_linalg.cuh).
+//
+//  * parallel == 0  (or one time chunk): the CTA runs the predict/update recursion over all T.
+//  * parallel == 1 with n > 1 time chunks -- a chunked prefix scan over the reference's
+//    associative 5-tuple elements (A, b, C, eta, J):
+//      pass A  chunk 0 runs the recursion directly (its aggregate's (b, C) IS the filtering
+//              marginal); chunks 1..n-2 build their elements (_filtering_init_one) and left-fold
+//              them with the reference's combine operator (_filtering_op_impl);
+//      pass B  one CTA per unit scans the (b, C) prefix across chunk aggregates;
+//      pass C  chunks 1..n-1 run the recursion from their incoming prefix, which also yields
+//              the log-likelihood increments the reference obtains from a second vmapped
+//              sequential_predict_update pass (filtering.py:60-62).
+//
+// Missing observations (non-finite y entries) are handled by the mathematical row mask the
+// reference emulates with infinite variances (filtering.py:86-101): masked rows of H, c are
+// zeroed, masked rows/cols of R become unit rows, and masked dimensions are excluded from the
+// Gaussian normaliser; a fully missing y_t is a pure prediction step (filtering.py:127-130).
+#include "common.cuh"
+#include "smem_linalg.cuh"
+
+namespace auxssm {
+
+template <typename T> struct FilterArgs {
+  auxssm_lgssm_desc d;
+  const T *ys, *m0, *P0, *Fs, *Qs, *bs, *Hs, *Rs, *cs;
+  T *ms, *Ps;
+  T* ellpart;  // [units][n_chunks]
+  T* prefix;   // [units][n_chunks][dx + dx*dx]   filtering marginal at the END of chunk j
+  T* agg;      // [units][n_chunks][3 dx^2 + 2 dx] chunk aggregates (A, C, J, b, eta)
+  int n_chunks, chunk_len;
+};
+
+template <typename T, int D> struct Carve {
+  T* p;
+  __device__ T* mat() { T* r = p; p += D * Tile<D>::LD; return r; }
+  __device__ T* vec() { T* r = p; p += D; return r; }
+};
+
+template <typename T, int D> struct StepBuf {
+  T *P, *W, *S, *U, *Ft, *Q, *Ht, *R;
+  T *m, *bv, *y, *c, *v, *dg;
+  int* mask;
+  T* red;
+  bool h_clean, r_clean, c_clean;
+};
+
+template <typename T> __device__ __forceinline__ T half_log_2pi() { return T(0.91893853320467274178); }
+
+// ---- staging ---------------------------------------------------------------------------------
+
+template <typename T, int D>
+__device__ __forceinline__ void stage_dyn(const FilterArgs<T>& a, int c, int b, int tm1, bool first, T* Ft, T* Fp,
+                                          T* Q, T* bv) {
+  const int dx = a.d.dx;
+  cta_sync<D>();
+  if (first || a.d.Fs.time != 0) {
+    const T* g = a.Fs + unit_off(a.d.Fs, c, b) + (int64_t)tm1 * a.d.Fs.time;
+    if (Ft) load_mat<T, D, true>(g, Ft, dx, dx);
+    if (Fp) load_mat<T, D, false>(g, Fp, dx, dx);
+  }
+  if (first || a.d.Qs.time != 0)
+    load_mat<T, D, false>(a.Qs + unit_off(a.d.Qs, c, b) + (int64_t)tm1 * a.d.Qs.time, Q, dx, dx);
+  if (first || a.d.bs.time != 0) {
+    const T* g = a.bs + unit_off(a.d.bs, c, b) + (int64_t)tm1 * a.d.bs.time;
+    if (threadIdx.x < dx) bv[threadIdx.x] = g[threadIdx.x];
+  }
+  cta_sync<D>();
+}
+
+// Stages y_t, H_t (transposed into Ht and/or plain into Hp), R_t, c_t with the missing-row mask
+// applied.  Returns the number of observed (finite) entries of y_t.
+template <typename T, int D>
+__device__ __forceinline__ int stage_obs(const FilterArgs<T>& a, int c, int b, int t, bool first, StepBuf<T, D>& s,
+                                         T* Hp, bool explicit_identity) {
+  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  const int dx = a.d.dx, dy = a.d.dy;
+  const bool hid = (a.d.flags & AUXSSM_FLAG_H_IDENTITY) != 0;
+  cta_sync<D>();
+  if (threadIdx.x < dy) {
+    const T yv = a.ys[unit_off(a.d.ys, c, b) + (int64_t)t * a.d.ys.time + threadIdx.x];
+    s.y[threadIdx.x] = yv;
+    s.mask[threadIdx.x] = finite_(yv) ? 0 : 1;
+  }
+  cta_sync<D>();
+  int n_mask = 0;
+  for (int i = 0; i < dy; ++i) n_mask += s.mask[i];
+  const bool any_mask = n_mask > 0;
+  if (first || any_mask || !s.h_clean || (!hid && a.d.Hs.time != 0)) {
+    if (hid) {
+      if (explicit_identity) {
+        for (int e = threadIdx.x; e < dy * dx; e += NT) {
+          const int i = e / dx, j = e % dx;
+          const T v = (i == j && !s.mask[i]) ? T(1) : T(0);
+          if (s.Ht) s.Ht[j * LD + i] = v;
+          if (Hp) Hp[i * LD + j] = v;
+        }
+      }
+    } else {
+      const T* g = a.Hs + unit_off(a.d.Hs, c, b) + (int64_t)t * a.d.Hs.time;
+      for (int e = threadIdx.x; e < dy * dx; e += NT) {
+        const int i = e / dx, j = e % dx;
+        const T v = s.mask[i] ? T(0) : g[e];
+        if (s.Ht) s.Ht[j * LD + i] = v;
+        if (Hp) Hp[i * LD + j] = v;
+      }
+    }
+    s.h_clean = !any_mask;
+  }
+  if (first || any_mask || !s.r_clean || a.d.Rs.time != 0) {
+    const T* g = a.Rs + unit_off(a.d.Rs, c, b) + (int64_t)t * a.d.Rs.time;
+    for (int e = threadIdx.x; e < dy * dy; e += NT) {
+      const int i = e / dy, j = e % dy;
+      T v = g[e];
+      if (s.mask[i] || s.mask[j]) v = (i == j) ? T(1) : T(0);
+      s.R[i * LD + j] = v;
+    }
+    s.r_clean = !any_mask;
+  }
+  if (first || any_mask || !s.c_clean || a.d.cs.time != 0) {
+    if (threadIdx.x < dy) {
+      T v = T(0);
+      if (a.cs != nullptr) v = a.cs[unit_off(a.d.cs, c, b) + (int64_t)t * a.d.cs.time + threadIdx.x];
+      s.c[threadIdx.x] = s.mask[threadIdx.x] ? T(0) : v;
+    }
+    s.c_clean = !any_mask;
+  }
+  cta_sync<D>();
+  return dy - n_mask;
+}
+
+// ---- the sequential recursion ------------------------------------------------------------------
+
+// (m, P) <- (F m + b, F P F^T + Q), symmetrised.  filtering.py:135-139.
+template <typename T, int D> __device__ __forceinline__ void kalman_predict(StepBuf<T, D>& s, int dx) {
+  mm_tn<T, D, 0>(s.P, s.Ft, s.W, nullptr, dx);   // W = P F^T   (P symmetric)
+  mm_tn<T, D, 1>(s.Ft, s.W, s.P, s.Q, dx);       // P = F W + Q
+  mv_tn<T, D, 1>(s.Ft, s.m, s.m, s.bv, dx, dx);  // m = F m + b
+  symmetrize<T, D>(s.P, dx);
+}
+
+// Measurement update with the masked observation staged in s; returns the log-likelihood
+// increment (uniform over the CTA).  filtering.py:84-130, with  Z = L^{-1} H P  so that
+// G S G^T = Z^T Z  and  G (y - yhat) = Z^T L^{-1} (y - yhat).
+template <typename T, int D, bool HID>
+__device__ __forceinline__ T kalman_update(StepBuf<T, D>& s, int dx, int dy, int n_obs) {
+  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  const int i = threadIdx.x;
+  if (HID) {
+    cta_sync<D>();
+    if (i < dy) s.v[i] = s.mask[i] ? T(0) : s.y[i] - s.m[i] - s.c[i];
+    for (int e = i; e < dy * dx; e += NT) {
+      const int r = e / dx, q = e % dx;
+      const T p = s.P[r * LD + q];
+      s.U[r * LD + q] = s.mask[r] ? T(0) : p;
+      s.S[r * LD + q] = (s.mask[r] || s.mask[q]) ? s.R[r * LD + q] : p + s.R[r * LD + q];
+    }
+    cta_sync<D>();
+  } else {
+    mv_tn<T, D, 0>(s.Ht, s.m, s.v, nullptr, dx, dy);  // v = H m
+    if (i < dy) s.v[i] = s.mask[i] ? T(0) : s.y[i] - s.v[i] - s.c[i];
+    mm_tn<T, D, 0>(s.Ht, s.P, s.U, nullptr, dx);      // U = H P            (dy x dx)
+    transpose_to<T, D>(s.U, s.W, dy, dx);             // W = U^T = P H^T    (dx x dy)
+    mm_tn<T, D, 1>(s.W, s.Ht, s.S, s.R, dx);          // S = H P H^T + R
+  }
+  chol_inplace<T, D>(s.S, s.dg, dy);
+  fwd_solve<T, D>(s.S, s.U, s.v, dy, dx);             // U <- Z = L^{-1} U ; v <- L^{-1} (y - yhat)
+  mm_tn<T, D, 2>(s.U, s.U, s.P, s.P, dy);             // P -= Z^T Z
+  mv_tn<T, D, 1>(s.U, s.v, s.m, s.m, dy, dx);         // m += Z^T v
+  symmetrize<T, D>(s.P, dx);
+  T part = T(0);
+  if (i < dy && !s.mask[i]) part = T(-0.5) * s.v[i] * s.v[i] - log(s.dg[i]);
+  T ell = cta_sum<T, D>(part, s.red) - T(n_obs) * half_log_2pi<T>();
+  if (!(ell == ell)) ell = T(0);  // nan_to_num(ell_inc, nan=0.), filtering.py:125
+  return ell;
+}
+
+template <typename T, int D> __device__ __forceinline__ void store_state(const FilterArgs<T>& a, int c, int b, int t,
+                                                                         const StepBuf<T, D>& s) {
+  const int dx = a.d.dx;
+  cta_sync<D>();
+  T* gm = a.ms + unit_off(a.d.ms, c, b) + (int64_t)t * a.d.ms.time;
+  if (threadIdx.x < dx) gm[threadIdx.x] = s.m[threadIdx.x];
+  store_mat<T, D>(a.Ps + unit_off(a.d.Ps, c, b) + (int64_t)t * a.d.Ps.time, s.P, dx, dx);
+}
+
+template <typename T, int D> __device__ __forceinline__ StepBuf<T, D> carve_step(Carve<T, D>& cv, bool hid) {
+  StepBuf<T, D> s;
+  s.P = cv.mat(); s.W = cv.mat(); s.S = cv.mat(); s.U = cv.mat();
+  s.Ft = cv.mat(); s.Q = cv.mat(); s.R = cv.mat();
+  s.Ht = hid ? nullptr : cv.mat();
+  s.m = cv.vec(); s.bv = cv.vec(); s.y = cv.vec(); s.c = cv.vec(); s.v = cv.vec(); s.dg = cv.vec();
+  s.red = cv.vec();
+  s.mask = reinterpret_cast<int*>(cv.p);
+  cv.p += (D * sizeof(int) + sizeof(T) - 1) / sizeof(T);
+  s.h_clean = s.r_clean = s.c_clean = false;
+  return s;
+}
+
+template <int D> __host__ __device__ constexpr size_t step_smem_elems(bool hid) {
+  return (size_t)(hid ? 7 : 8) * D * Tile<D>::LD + 7 * D + D /* mask, generous */ + 16;
+}
+
+// Runs t = t_begin .. t_end-1 of the recursion starting from the state in s (valid for t_begin-1),
+// or from the prior (m0, P0) with the t = 0 update when t_begin == 0.  Returns the summed ell.
+template <typename T, int D, bool HID>
+__device__ __forceinline__ T run_recursion(const FilterArgs<T>& a, int c, int b, int t_begin, int t_end,
+                                           StepBuf<T, D>& s) {
+  const int dx = a.d.dx, dy = a.d.dy;
+  T ell = T(0);
+  bool first_dyn = true, first_obs = true;
+  int t = t_begin;
+  if (t == 0) {
+    cta_sync<D>();
+    if (threadIdx.x < dx) s.m[threadIdx.x] = a.m0[unit_off(a.d.m0, c, b) + threadIdx.x];
+    load_mat<T, D, false>(a.P0 + unit_off(a.d.P0, c, b), s.P, dx, dx);
+    const int n_obs = stage_obs<T, D>(a, c, b, 0, true, s, nullptr, false);
+    first_obs = false;
+    if (n_obs > 0) ell += kalman_update<T, D, HID>(s, dx, dy, n_obs);
+    store_state<T, D>(a, c, b, 0, s);
+    t = 1;
+  }
+  for (; t < t_end; ++t) {
+    stage_dyn<T, D>(a, c, b, t - 1, first_dyn, s.Ft, nullptr, s.Q, s.bv);
+    first_dyn = false;
+    const int n_obs = stage_obs<T, D>(a, c, b, t, first_obs, s, nullptr, false);
+    first_obs = false;
+    kalman_predict<T, D>(s, dx);
+    if (n_obs > 0) ell += kalman_update<T, D, HID>(s, dx, dy, n_obs);
+    store_state<T, D>(a, c, b, t, s);
+  }
+  return ell;
+}
+
+__device__ __forceinline__ void chunk_range(int j, int chunk_len, int T, int& t0, int& t1) {
+  // chunk j covers scan elements t in [1 + j*len, 1 + (j+1)*len) ; chunk 0 additionally owns t = 0
+  t0 = (j == 0) ? 0 : 1 + j * chunk_len;
+  t1 = 1 + (j + 1) * chunk_len;
+  if (t1 > T) t1 = T;
+}
+
+// pass A (chunk 0) and pass C (chunks >= 1): the recursion over one chunk.
+template <typename T, int D, bool HID>
+__global__ void __launch_bounds__(Tile<D>::NT) filter_recursion_kernel(FilterArgs<T> a, int chunk_first) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Carve<T, D> cv{reinterpret_cast<T*>(smem_raw)};
+  constexpr int NT = Tile<D>::NT;
+  const size_t total = step_smem_elems<D>(HID);
+  for (size_t e = threadIdx.x; e < total; e += NT) cv.p[e] = T(0);
+  __syncthreads();
+  StepBuf<T, D> s = carve_step<T, D>(cv, HID);
+  const int j = chunk_first + blockIdx.y;
+  const int unit = blockIdx.x;
+  const int c = unit / a.d.n_batch, b = unit % a.d.n_batch;
+  const int dx = a.d.dx;
+  int t0, t1;
+  chunk_range(j, a.chunk_len, a.d.T, t0, t1);
+  const int psz = dx + dx * dx;
+  if (j > 0) {
+    const T* pf = a.prefix + ((int64_t)unit * a.n_chunks + (j - 1)) * psz;
+    if (threadIdx.x < dx) s.m[threadIdx.x] = pf[threadIdx.x];
+    load_mat<T, D, false>(pf + dx, s.P, dx, dx);
+  }
+  const T ell = run_recursion<T, D, HID>(a, c, b, t0, t1, s);
+  cta_sync<D>();
+  if (j + 1 < a.n_chunks && j == 0) {
+    T* pf = a.prefix + ((int64_t)unit * a.n_chunks + j) * psz;
+    if (threadIdx.x < dx) pf[threadIdx.x] = s.m[threadIdx.x];
+    store_mat<T, D>(pf + dx, s.P, dx, dx);
+  }
+  if (threadIdx.x == 0) a.ellpart[(int64_t)unit * a.n_chunks + j] = ell;
+}
+
+// ---- parallel-in-time: elements and the associative combine ------------------------------------
+
+template <typename T, int D> struct ScanBuf {
+  T *A1, *C1, *J1;        // running aggregate (A plain)
+  T *A2t, *C2, *J2;       // current element (A transposed)
+  T *B1, *B2, *B3, *B4, *B5, *B6, *B7;
+  T *b1, *e1, *b2, *e2, *w, *tmp;
+  int* perm;
+  int* ired;
+};
+
+template <int D> __host__ __device__ constexpr size_t scan_smem_elems() {
+  return (size_t)13 * D * Tile<D>::LD + 6 * D + 7 * D + D + 2 * D /* perm, ired */ + 32;
+}
+
+// Element (A, b, C, eta, J) of time step t (t >= 1, not the first element of the scan), with A
+// stored TRANSPOSED in sc.A2t.  _filtering_init_one (filtering.py:197-250) with m = 0, P = 0, i.e.
+// m^- = b, P^- = Q.  Uses B1..B7 and the StepBuf vectors as scratch.
+template <typename T, int D>
+__device__ __forceinline__ void build_element(const FilterArgs<T>& a, int c, int b, int t, StepBuf<T, D>& s,
+                                              ScanBuf<T, D>& sc) {
+  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  const int dx = a.d.dx, dy = a.d.dy, i = threadIdx.x;
+  T* F = sc.B1; T* Ft = sc.B2; T* Ht = sc.B3; T* Hp = sc.B4; T* S = sc.B5; T* Ut = sc.B6; T* Z = sc.B7;
+  // stage (always reloaded: the scratch buffers are recycled by the combine)
+  stage_dyn<T, D>(a, c, b, t - 1, true, Ft, F, sc.C2, sc.b2);  // C2 <- Q (= P^-), b2 <- b (= m^-)
+  s.Ht = Ht; s.R = S;
+  for (int e = i; e < D * LD; e += NT) { Ht[e] = T(0); Hp[e] = T(0); S[e] = T(0); }
+  const int n_obs = stage_obs<T, D>(a, c, b, t, true, s, Hp, true);
+  if (n_obs == 0) {  // _passthrough, filtering.py:239-248
+    copy_mat<T, D>(Ft, sc.A2t, dx, dx);
+    for (int e = i; e < D * LD; e += NT) sc.J2[e] = T(0);
+    if (i < dx) sc.e2[i] = T(0);
+    symmetrize<T, D>(sc.C2, dx);
+    return;
+  }
+  mv_tn<T, D, 0>(Ht, sc.b2, s.v, nullptr, dx, dy);                 // v = H b
+  if (i < dy) s.v[i] = s.mask[i] ? T(0) : s.y[i] - s.v[i] - s.c[i];  // y - H b - c
+  mm_tn<T, D, 0>(sc.C2, Ht, Ut, nullptr, dx);                      // Ut = Q H^T          (dx x dy)
+  mm_tn<T, D, 1>(Ht, Ut, S, S, dx);                                // S = H Q H^T + R
+  transpose_to<T, D>(Ut, Z, dx, dy);                               // Z <- U = H Q        (dy x dx)
+  chol_inplace<T, D>(S, s.dg, dy);
+  fwd_solve<T, D>(S, Z, s.v, dy, dx);                              // Z = L^{-1} H Q ; v = L^{-1}(y - Hb - c)
+  fwd_solve<T, D>(S, Hp, nullptr, dy, dx);                         // Hp <- Zh = L^{-1} H
+  mm_tn<T, D, 2>(Z, Z, sc.C2, sc.C2, dy);                          // C = Q - Z^T Z
+  mv_tn<T, D, 1>(Z, s.v, sc.b2, sc.b2, dy, dx);                    // b = b + Z^T v
+  symmetrize<T, D>(sc.C2, dx);
+  mm_tn<T, D, 0>(Hp, Z, Ut, nullptr, dy);                          // Ut <- (K H)^T = Zh^T Z
+  mm_tn<T, D, 2>(F, Ut, sc.A2t, Ft, dx);                           // A^T = F^T - F^T (K H)^T
+  mm_tn<T, D, 0>(Hp, Hp, Ut, nullptr, dy);                         // N = Zh^T Zh = H^T S^{-1} H
+  mm_tn<T, D, 0>(Ut, F, Z, nullptr, dx);                           // Z <- N F
+  mm_tn<T, D, 0>(F, Z, sc.J2, nullptr, dx);                        // J = F^T N F
+  symmetrize<T, D>(sc.J2, dx);
+  mv_tn<T, D, 0>(Hp, s.v, sc.tmp, nullptr, dy, dx);                // tmp = Zh^T v = H^T S^{-1}(y - Hb - c)
+  mv_tn<T, D, 0>(F, sc.tmp, sc.e2, nullptr, dx, dx);               // eta = F^T tmp
+}
+
+// (A1, b1, C1, eta1, J1) <- (A1, ...) (x) (A2, b2, C2, eta2, J2).   _filtering_op_impl,
+// filtering.py:164-183, with one LU of M = I + C1 J2 serving every solve:
+//   V = M^{-1} A1, Dm = M^{-1} C1, w = M^{-1}(b1 + C1 eta2);
+//   A = A2 V; b = A2 w + b2; C = A2 Dm A2^T + C2; eta = V^T (eta2 - J2 b1) + eta1; J = V^T J2 A1 + J1.
+// `full` = false skips A, eta, J (enough when only the (b, C) prefix is needed).
+template <typename T, int D>
+__device__ __forceinline__ void combine(ScanBuf<T, D>& sc, T* red, int dx, bool full) {
+  constexpr int LD = Tile<D>::LD;
+  const int i = threadIdx.x;
+  T* M = sc.B1; T* V = sc.B2; T* Dm = sc.B3; T* An = sc.B4; T* W = sc.B5;
+  mm_tn<T, D, 0>(sc.C1, sc.J2, M, nullptr, dx);  // C1 J2
+  if (i < dx) M[i * LD + i] += T(1);
+  mv_tn<T, D, 1>(sc.C1, sc.e2, sc.w, sc.b1, dx, dx);  // w = b1 + C1 eta2
+  lu_inplace<T, D>(M, sc.perm, red, sc.ired, dx);
+  lu_solve<T, D>(M, sc.perm, sc.C1, Dm, sc.w, sc.tmp, dx, dx);  // Dm = M^{-1} C1 ; tmp = M^{-1} w
+  if (full) {
+    lu_solve<T, D>(M, sc.perm, sc.A1, V, nullptr, nullptr, dx, dx);  // V = M^{-1} A1
+    mm_tn<T, D, 0>(sc.J2, sc.A1, W, nullptr, dx);                    // W = J2 A1
+    mm_tn<T, D, 1>(V, W, sc.J1, sc.J1, dx);                          // J = V^T W + J1
+    symmetrize<T, D>(sc.J1, dx);
+    mv_tn<T, D, 2>(sc.J2, sc.b1, sc.w, sc.e2, dx, dx);               // w = eta2 - J2 b1
+    mv_tn<T, D, 1>(V, sc.w, sc.e1, sc.e1, dx, dx);                   // eta = V^T w + eta1
+    mm_tn<T, D, 0>(sc.A2t, V, An, nullptr, dx);                      // A = A2 V
+  }
+  mv_tn<T, D, 1>(sc.A2t, sc.tmp, sc.b1, sc.b2, dx, dx);              // b = A2 M^{-1}(b1 + C1 eta2) + b2
+  mm_tn<T, D, 0>(Dm, sc.A2t, W, nullptr, dx);                        // W = Dm^T A2^T
+  mm_tn<T, D, 1>(sc.A2t, W, sc.C1, sc.C2, dx);                       // C = A2 W + C2
+  symmetrize<T, D>(sc.C1, dx);
+  if (full) { T* t = sc.A1; sc.A1 = An; sc.B4 = t; }
+}
+
+template <typename T, int D> __device__ __forceinline__ ScanBuf<T, D> carve_scan(Carve<T, D>& cv) {
+  ScanBuf<T, D> sc;
+  sc.A1 = cv.mat(); sc.C1 = cv.mat(); sc.J1 = cv.mat();
+  sc.A2t = cv.mat(); sc.C2 = cv.mat(); sc.J2 = cv.mat();
+  sc.B1 = cv.mat(); sc.B2 = cv.mat(); sc.B3 = cv.mat(); sc.B4 = cv.mat(); sc.B5 = cv.mat();
+  sc.B6 = cv.mat(); sc.B7 = cv.mat();
+  sc.b1 = cv.vec(); sc.e1 = cv.vec(); sc.b2 = cv.vec(); sc.e2 = cv.vec(); sc.w = cv.vec(); sc.tmp = cv.vec();
+  return sc;
+}
+
+template <typename T, int D>
+__device__ __forceinline__ void carve_scan_tail(Carve<T, D>& cv, StepBuf<T, D>& s, ScanBuf<T, D>& sc) {
+  s.P = s.W = s.S = s.U = s.Ft = s.Q = s.Ht = s.R = nullptr;
+  s.m = cv.vec(); s.bv = cv.vec(); s.y = cv.vec(); s.c = cv.vec(); s.v = cv.vec(); s.dg = cv.vec(); s.red = cv.vec();
+  s.mask = reinterpret_cast<int*>(cv.p);
+  cv.p += (D * sizeof(int) + sizeof(T) - 1) / sizeof(T);
+  sc.perm = reinterpret_cast<int*>(cv.p);
+  cv.p += (D * sizeof(int) + sizeof(T) - 1) / sizeof(T);
+  sc.ired = reinterpret_cast<int*>(cv.p);
+  cv.p += (D * sizeof(int) + sizeof(T) - 1) / sizeof(T);
+  s.h_clean = s.r_clean = s.c_clean = false;
+}
+
+// pass A for chunks 1..n-2: aggregate = elem(t0) (x) elem(t0+1) (x) ... (x) elem(t1-1)
+template <typename T, int D>
+__global__ void __launch_bounds__(Tile<D>::NT) filter_aggregate_kernel(FilterArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Carve<T, D> cv{reinterpret_cast<T*>(smem_raw)};
+  constexpr int NT = Tile<D>::NT;
+  const size_t total = scan_smem_elems<D>();
+  for (size_t e = threadIdx.x; e < total; e += NT) cv.p[e] = T(0);
+  __syncthreads();
+  ScanBuf<T, D> sc = carve_scan<T, D>(cv);
+  StepBuf<T, D> s;
+  carve_scan_tail<T, D>(cv, s, sc);
+  const int j = 1 + blockIdx.y;
+  const int unit = blockIdx.x;
+  const int c = unit / a.d.n_batch, b = unit % a.d.n_batch;
+  const int dx = a.d.dx;
+  int t0, t1;
+  chunk_range(j, a.chunk_len, a.d.T, t0, t1);
+  for (int t = t0; t < t1; ++t) {
+    build_element<T, D>(a, c, b, t, s, sc);
+    if (t == t0) {
+      transpose_to<T, D>(sc.A2t, sc.A1, dx, dx);
+      copy_mat<T, D>(sc.C2, sc.C1, dx, dx);
+      copy_mat<T, D>(sc.J2, sc.J1, dx, dx);
+      if (threadIdx.x < dx) { sc.b1[threadIdx.x] = sc.b2[threadIdx.x]; sc.e1[threadIdx.x] = sc.e2[threadIdx.x]; }
+      cta_sync<D>();
+    } else {
+      combine<T, D>(sc, s.red, dx, true);
+    }
+  }
+  cta_sync<D>();
+  const int esz = 3 * dx * dx + 2 * dx;
+  T* g = a.agg + ((int64_t)unit * a.n_chunks + j) * esz;
+  store_mat<T, D>(g, sc.A1, dx, dx);
+  store_mat<T, D>(g + dx * dx, sc.C1, dx, dx);
+  store_mat<T, D>(g + 2 * dx * dx, sc.J1, dx, dx);
+  if (threadIdx.x < dx) {
+    g[3 * dx * dx + threadIdx.x] = sc.b1[threadIdx.x];
+    g[3 * dx * dx + dx + threadIdx.x] = sc.e1[threadIdx.x];
+  }
+}
+
+// pass B: prefix_j = prefix_{j-1} (x) aggregate_j for j = 1..n-2, (b, C) components only.
+template <typename T, int D>
+__global__ void __launch_bounds__(Tile<D>::NT) filter_prefix_kernel(FilterArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Carve<T, D> cv{reinterpret_cast<T*>(smem_raw)};
+  constexpr int NT = Tile<D>::NT;
+  const size_t total = scan_smem_elems<D>();
+  for (size_t e = threadIdx.x; e < total; e += NT) cv.p[e] = T(0);
+  __syncthreads();
+  ScanBuf<T, D> sc = carve_scan<T, D>(cv);
+  StepBuf<T, D> s;
+  carve_scan_tail<T, D>(cv, s, sc);
+  const int unit = blockIdx.x;
+  const int dx = a.d.dx;
+  const int psz = dx + dx * dx, esz = 3 * dx * dx + 2 * dx;
+  T* pf = a.prefix + (int64_t)unit * a.n_chunks * psz;
+  if (threadIdx.x < dx) sc.b1[threadIdx.x] = pf[threadIdx.x];
+  load_mat<T, D, false>(pf + dx, sc.C1, dx, dx);
+  for (int j = 1; j + 1 < a.n_chunks; ++j) {
+    const T* g = a.agg + ((int64_t)unit * a.n_chunks + j) * esz;
+    cta_sync<D>();
+    load_mat<T, D, true>(g, sc.A2t, dx, dx);
+    load_mat<T, D, false>(g + dx * dx, sc.C2, dx, dx);
+    load_mat<T, D, false>(g + 2 * dx * dx, sc.J2, dx, dx);
+    if (threadIdx.x < dx) {
+      sc.b2[threadIdx.x] = g[3 * dx * dx + threadIdx.x];
+      sc.e2[threadIdx.x] = g[3 * dx * dx + dx + threadIdx.x];
+    }
+    cta_sync<D>();
+    combine<T, D>(sc, s.red, dx, false);
+    T* po = pf + (int64_t)j * psz;
+    if (threadIdx.x < dx) po[threadIdx.x] = sc.b1[threadIdx.x];
+    store_mat<T, D>(po + dx, sc.C1, dx, dx);
+  }
+}
+
+// ell[c] = sum over inner batch and chunks, in a fixed order (deterministic).
+template <typename T> __global__ void ell_reduce_kernel(const T* ellpart, T* ell, int n_chains, int per_chain) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  T s = T(0);
+  for (int k = 0; k < per_chain; ++k) s += ellpart[(int64_t)c * per_chain + k];
+  ell[c] = s;
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct FilterPlan {
+  int n_chunks, chunk_len;
+  size_t off_ell, off_prefix, off_agg, total;
+};
+
+static FilterPlan make_plan(const auxssm_lgssm_desc* d, size_t es) {
+  FilterPlan p;
+  p.n_chunks = resolve_time_chunks(d);
+  const int n_elem = d->T > 1 ? d->T - 1 : 1;
+  p.chunk_len = (n_elem + p.n_chunks - 1) / p.n_chunks;
+  p.n_chunks = (n_elem + p.chunk_len - 1) / p.chunk_len;  // drop empty trailing chunks
+  const size_t units = (size_t)d->n_chains * d->n_batch;
+  size_t off = 0;
+  p.off_ell = off; off = align_up(off + units * p.n_chunks * es, 256);
+  p.off_prefix = off;
+  if (p.n_chunks > 1) off = align_up(off + units * p.n_chunks * ((size_t)d->dx + (size_t)d->dx * d->dx) * es, 256);
+  p.off_agg = off;
+  if (p.n_chunks > 2) off = align_up(off + units * p.n_chunks * (3 * (size_t)d->dx * d->dx + 2 * (size_t)d->dx) * es, 256);
+  p.total = off;
+  return p;
+}
+
+template <typename T, int D>
+static int launch_filter(cudaStream_t st, const FilterArgs<T>& a) {
+  const bool hid = (a.d.flags & AUXSSM_FLAG_H_IDENTITY) != 0;
+  const int units = a.d.n_chains * a.d.n_batch;
+  constexpr int NT = Tile<D>::NT;
+  const size_t smem_step = step_smem_elems<D>(hid) * sizeof(T);
+  auto rec = hid ? filter_recursion_kernel<T, D, true> : filter_recursion_kernel<T, D, false>;
+  int rc = ensure_smem(rec, smem_step, "auxssm_kalman_filter");
+  if (rc) return rc;
+  rec<<<dim3(units, 1), NT, smem_step, st>>>(a, 0);
+  AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (recursion, chunk 0)");
+  if (a.n_chunks > 1) {
+    const size_t smem_scan = scan_smem_elems<D>() * sizeof(T);
+    if (a.n_chunks > 2) {
+      rc = ensure_smem(filter_aggregate_kernel<T, D>, smem_scan, "auxssm_kalman_filter (parallel)");
+      if (rc) return rc;
+      rc = ensure_smem(filter_prefix_kernel<T, D>, smem_scan, "auxssm_kalman_filter (parallel)");
+      if (rc) return rc;
+      filter_aggregate_kernel<T, D><<<dim3(units, a.n_chunks - 2), NT, smem_scan, st>>>(a);
+      AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (aggregate)");
+      filter_prefix_kernel<T, D><<<units, NT, smem_scan, st>>>(a);
+      AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (prefix)");
+    }
+    rec<<<dim3(units, a.n_chunks - 1), NT, smem_step, st>>>(a, 1);
+    AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (recursion, chunks >= 1)");
+  }
+  return AUXSSM_OK;
+}
+
+template <typename T>
+static int filter_entry(void* stream, const auxssm_lgssm_desc* d, const T* ys, const T* m0, const T* P0, const T* Fs,
+                        const T* Qs, const T* bs, const T* Hs, const T* Rs, const T* cs, T* ms, T* Ps, T* ell,
+                        void* scratch, size_t scratch_bytes) {
+  const char* who = "auxssm_kalman_filter";
+  int rc = check_desc(d, who);
+  if (rc) return rc;
+  const bool hid = (d->flags & AUXSSM_FLAG_H_IDENTITY) != 0;
+  if (!ys || !m0 || !P0 || !Rs || !ms || !Ps || !ell || (!hid && !Hs) ||
+      (d->T > 1 && (!Fs || !Qs || !bs))) {
+    set_error("%s: null data pointer", who);
+    return AUXSSM_ERR_INVALID;
+  }
+  if (hid && Hs != nullptr) { set_error("%s: Hs must be NULL with AUXSSM_FLAG_H_IDENTITY", who); return AUXSSM_ERR_INVALID; }
+  const FilterPlan p = make_plan(d, sizeof(T));
+  if (scratch_bytes < p.total || (p.total > 0 && scratch == nullptr)) {
+    set_error("%s: scratch too small (%zu < %zu bytes)", who, scratch_bytes, p.total);
+    return AUXSSM_ERR_SCRATCH;
+  }
+  FilterArgs<T> a;
+  a.d = *d;
+  a.ys = ys; a.m0 = m0; a.P0 = P0; a.Fs = Fs; a.Qs = Qs; a.bs = bs; a.Hs = Hs; a.Rs = Rs; a.cs = cs;
+  a.ms = ms; a.Ps = Ps;
+  unsigned char* sb = static_cast<unsigned char*>(scratch);
+  a.ellpart = reinterpret_cast<T*>(sb + p.off_ell);
+  a.prefix = reinterpret_cast<T*>(sb + p.off_prefix);
+  a.agg = reinterpret_cast<T*>(sb + p.off_agg);
+  a.n_chunks = p.n_chunks;
+  a.chunk_len = p.chunk_len;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int dmax = d->dx > d->dy ? d->dx : d->dy;
+  switch (padded_dim(dmax)) {
+    case 4: rc = launch_filter<T, 4>(st, a); break;
+    case 8: rc = launch_filter<T, 8>(st, a); break;
+    case 16: rc = launch_filter<T, 16>(st, a); break;
+    case 32: rc = launch_filter<T, 32>(st, a); break;
+    case 64: rc = launch_filter<T, 64>(st, a); break;
+    default: set_error("%s: unsupported dimension %d", who, dmax); return AUXSSM_ERR_UNSUPPORTED;
+  }
+  if (rc) return rc;
+  ell_reduce_kernel<T><<<(d->n_chains + 127) / 128, 128, 0, st>>>(a.ellpart, ell, d->n_chains,
+                                                                  d->n_batch * p.n_chunks);
+  AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (ell reduce)");
+  return AUXSSM_OK;
+}
+
+}  // namespace auxssm
+
+extern "C" __attribute__((visibility("default"))) size_t auxssm_kalman_filter_scratch_bytes(const auxssm_lgssm_desc* desc, int32_t elem_size) {
+  if (auxssm::check_desc(desc, "auxssm_kalman_filter_scratch_bytes")) return 0;
+  return auxssm::make_plan(desc, (size_t)elem_size).total;
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t auxssm_kalman_filter_f32(void* stream, const auxssm_lgssm_desc* desc, const float* ys,
+                                            const float* m0, const float* P0, const float* Fs, const float* Qs,
+                                            const float* bs, const float* Hs, const float* Rs, const float* cs,
+                                            float* ms, float* Ps, float* ell, void* scratch, size_t scratch_bytes) {
+  return auxssm::filter_entry<float>(stream, desc, ys, m0, P0, Fs, Qs, bs, Hs, Rs, cs, ms, Ps, ell, scratch,
+                                     scratch_bytes);
+}
+extern "C" __attribute__((visibility("default"))) int32_t auxssm_kalman_filter_f64(void* stream, const auxssm_lgssm_desc* desc, const double* ys,
+                                            const double* m0, const double* P0, const double* Fs, const double* Qs,
+                                            const double* bs, const double* Hs, const double* Rs, const double* cs,
+                                            double* ms, double* Ps, double* ell, void* scratch,
+                                            size_t scratch_bytes) {
+  return auxssm::filter_entry<double>(stream, desc, ys, m0, P0, Fs, Qs, bs, Hs, Rs, cs, ms, Ps, ell, scratch,
+                                      scratch_bytes);
+}

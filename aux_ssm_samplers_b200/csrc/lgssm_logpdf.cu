@@ -1,0 +1,249 @@
+// Trajectory log-densities of a linear-Gaussian state-space model.
+//
+// Replaces aux_samplers/_primitives/kalman/base.py of the reference: posterior_logpdf:73-96,
+// prior_logpdf:100-134, log_likelihood:138-166, with the Cholesky-parametrised Gaussian density of
+// aux_samplers/_primitives/math/mvn/base.py:16-58 and its nansum conventions (a NaN term -- e.g. a
+// missing observation -- contributes 0).
+//
+// One CTA per (unit, time tile); the per-step terms are summed in time order inside the CTA and the
+// per-tile partial sums are reduced in a fixed order by a second tiny kernel (deterministic).
+// Cholesky factors of time-invariant Q / R are computed once per CTA.
+#include "common.cuh"
+#include "smem_linalg.cuh"
+
+namespace auxssm {
+
+template <typename T> struct LogpdfArgs {
+  auxssm_lgssm_desc d;
+  uint32_t which;
+  const T *ys, *xs, *ell, *m0, *P0, *Fs, *Qs, *bs, *Hs, *Rs, *cs;
+  T* out;
+  T* partial;  // [units][n_tiles]
+  int n_tiles, tile_len;
+};
+
+template <typename T> __device__ __forceinline__ T half_log_2pi_() { return T(0.91893853320467274178); }
+
+// log N(r; 0, L L^T) for the residual in `r` (overwritten), mvn/base.py:16-58: non-finite diagonal
+// entries of L are dropped from the dimension count and the log-determinant.  Uniform result.
+template <typename T, int D> __device__ __forceinline__ T gauss_logpdf(const T* L, T* r, T* red, int n) {
+  constexpr int LD = Tile<D>::LD;
+  fwd_solve<T, D>(L, nullptr, r, n, 0);
+  T part = T(0);
+  const int i = threadIdx.x;
+  if (i < n) {
+    const T lii = L[i * LD + i];
+    if (finite_(lii)) part = T(-0.5) * r[i] * r[i] - log(fabs(lii)) - half_log_2pi_<T>();
+  }
+  return cta_sum<T, D>(part, red);
+}
+
+template <int D> __host__ __device__ constexpr size_t logpdf_smem_elems() {
+  return (size_t)4 * D * Tile<D>::LD + 8 * D + 16;
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(Tile<D>::NT) lgssm_logpdf_kernel(LogpdfArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* p = reinterpret_cast<T*>(smem_raw);
+  constexpr int NT = Tile<D>::NT, LD = Tile<D>::LD;
+  for (size_t e = threadIdx.x; e < logpdf_smem_elems<D>(); e += NT) p[e] = T(0);
+  __syncthreads();
+  T* Ft = p; p += D * LD;
+  T* LQ = p; p += D * LD;
+  T* Ht = p; p += D * LD;
+  T* LR = p; p += D * LD;
+  T* xprev = p; p += D;
+  T* xcur = p; p += D;
+  T* r = p; p += D;
+  T* bv = p; p += D;
+  T* cv = p; p += D;
+  T* yv = p; p += D;
+  T* dg = p; p += D;
+  T* red = p; p += D;
+  const int unit = blockIdx.x, tile = blockIdx.y;
+  const int c = unit / a.d.n_batch, b = unit % a.d.n_batch;
+  const int dx = a.d.dx, dy = a.d.dy, Tn = a.d.T;
+  const bool hid = (a.d.flags & AUXSSM_FLAG_H_IDENTITY) != 0;
+  const bool do_prior = (a.which & AUXSSM_LOGPDF_PRIOR) != 0, do_lik = (a.which & AUXSSM_LOGPDF_LOGLIK) != 0;
+  const int t0 = tile * a.tile_len;
+  int t1 = t0 + a.tile_len;
+  if (t1 > Tn) t1 = Tn;
+  const int i = threadIdx.x;
+  T total = T(0);
+  bool first_dyn = true, first_obs = true;
+  for (int t = t0; t < t1; ++t) {
+    cta_sync<D>();
+    if (i < dx) {
+      const T* xg = a.xs + unit_off(a.d.xs, c, b);
+      xcur[i] = xg[(int64_t)t * a.d.xs.time + i];
+      if (t > 0 && t == t0) xprev[i] = xg[(int64_t)(t - 1) * a.d.xs.time + i];
+    }
+    cta_sync<D>();
+    if (do_prior) {
+      if (t == 0) {
+        load_mat<T, D, false>(a.P0 + unit_off(a.d.P0, c, b), LQ, dx, dx);
+        if (i < dx) r[i] = xcur[i] - a.m0[unit_off(a.d.m0, c, b) + i];
+        chol_inplace<T, D>(LQ, dg, dx);
+        T term = gauss_logpdf<T, D>(LQ, r, red, dx);
+        if (!(term == term)) term = T(0);
+        total += term;
+        first_dyn = true;  // LQ now holds chol(P0): force a reload of Q below
+      } else {
+        const int tm1 = t - 1;
+        if (first_dyn || a.d.Fs.time != 0)
+          load_mat<T, D, true>(a.Fs + unit_off(a.d.Fs, c, b) + (int64_t)tm1 * a.d.Fs.time, Ft, dx, dx);
+        if (first_dyn || a.d.bs.time != 0) {
+          if (i < dx) bv[i] = a.bs[unit_off(a.d.bs, c, b) + (int64_t)tm1 * a.d.bs.time + i];
+        }
+        if (first_dyn || a.d.Qs.time != 0) {
+          cta_sync<D>();
+          load_mat<T, D, false>(a.Qs + unit_off(a.d.Qs, c, b) + (int64_t)tm1 * a.d.Qs.time, LQ, dx, dx);
+          chol_inplace<T, D>(LQ, dg, dx);
+        }
+        first_dyn = false;
+        mv_tn<T, D, 1>(Ft, xprev, r, bv, dx, dx);  // r = F x_{t-1} + b
+        if (i < dx) r[i] = xcur[i] - r[i];
+        T term = gauss_logpdf<T, D>(LQ, r, red, dx);
+        if (!(term == term)) term = T(0);
+        total += term;
+      }
+    }
+    if (do_lik) {
+      if (!hid && (first_obs || a.d.Hs.time != 0)) {
+        cta_sync<D>();
+        load_mat<T, D, true>(a.Hs + unit_off(a.d.Hs, c, b) + (int64_t)t * a.d.Hs.time, Ht, dy, dx);
+      }
+      if (first_obs || a.d.cs.time != 0) {
+        if (i < dy) cv[i] = a.cs ? a.cs[unit_off(a.d.cs, c, b) + (int64_t)t * a.d.cs.time + i] : T(0);
+      }
+      if (first_obs || a.d.Rs.time != 0) {
+        cta_sync<D>();
+        load_mat<T, D, false>(a.Rs + unit_off(a.d.Rs, c, b) + (int64_t)t * a.d.Rs.time, LR, dy, dy);
+        chol_inplace<T, D>(LR, dg, dy);
+      }
+      first_obs = false;
+      if (i < dy) yv[i] = a.ys[unit_off(a.d.ys, c, b) + (int64_t)t * a.d.ys.time + i];
+      if (hid) {
+        cta_sync<D>();
+        if (i < dy) r[i] = yv[i] - xcur[i] - cv[i];
+      } else {
+        mv_tn<T, D, 1>(Ht, xcur, r, cv, dx, dy);  // r = H x + c
+        if (i < dy) r[i] = yv[i] - r[i];
+      }
+      T term = gauss_logpdf<T, D>(LR, r, red, dy);
+      if (!(term == term)) term = T(0);
+      total += term;
+    }
+    cta_sync<D>();
+    if (i < dx) xprev[i] = xcur[i];
+  }
+  if (threadIdx.x == 0) a.partial[(int64_t)unit * a.n_tiles + tile] = total;
+}
+
+template <typename T>
+__global__ void logpdf_reduce_kernel(const T* partial, const T* ell, T* out, int n_chains, int per_chain,
+                                     int minus_ell) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  T s = T(0);
+  for (int k = 0; k < per_chain; ++k) s += partial[(int64_t)c * per_chain + k];
+  if (minus_ell) s -= ell[c];
+  out[c] = s;
+}
+
+struct LogpdfPlan {
+  int n_tiles, tile_len;
+  size_t total;
+};
+
+static LogpdfPlan make_logpdf_plan(const auxssm_lgssm_desc* d, size_t es) {
+  LogpdfPlan p;
+  const long units = (long)d->n_chains * d->n_batch;
+  long want = (8L * device_sm_count() + units - 1) / units;
+  long cap = d->T / 8;
+  if (cap < 1) cap = 1;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  p.tile_len = (int)((d->T + want - 1) / want);
+  p.n_tiles = (d->T + p.tile_len - 1) / p.tile_len;
+  p.total = ((size_t)units * p.n_tiles * es + 255) / 256 * 256;
+  return p;
+}
+
+template <typename T, int D> static int launch_logpdf(cudaStream_t st, const LogpdfArgs<T>& a) {
+  const int units = a.d.n_chains * a.d.n_batch;
+  const size_t smem = logpdf_smem_elems<D>() * sizeof(T);
+  int rc = ensure_smem(lgssm_logpdf_kernel<T, D>, smem, "auxssm_lgssm_logpdf");
+  if (rc) return rc;
+  lgssm_logpdf_kernel<T, D><<<dim3(units, a.n_tiles), Tile<D>::NT, smem, st>>>(a);
+  AUXSSM_CHECK_LAUNCH("auxssm_lgssm_logpdf");
+  return AUXSSM_OK;
+}
+
+template <typename T>
+static int logpdf_entry(void* stream, const auxssm_lgssm_desc* d, uint32_t which, const T* ys, const T* xs,
+                        const T* ell, const T* m0, const T* P0, const T* Fs, const T* Qs, const T* bs, const T* Hs,
+                        const T* Rs, const T* cs, T* out, void* scratch, size_t scratch_bytes) {
+  const char* who = "auxssm_lgssm_logpdf";
+  int rc = check_desc(d, who);
+  if (rc) return rc;
+  const bool hid = (d->flags & AUXSSM_FLAG_H_IDENTITY) != 0;
+  const bool do_prior = (which & AUXSSM_LOGPDF_PRIOR) != 0, do_lik = (which & AUXSSM_LOGPDF_LOGLIK) != 0;
+  if (!xs || !out || (do_prior && (!m0 || !P0 || (d->T > 1 && (!Fs || !Qs || !bs)))) ||
+      (do_lik && (!ys || !Rs || (!hid && !Hs))) || ((which & AUXSSM_LOGPDF_MINUS_ELL) && !ell)) {
+    set_error("%s: null data pointer", who);
+    return AUXSSM_ERR_INVALID;
+  }
+  const LogpdfPlan p = make_logpdf_plan(d, sizeof(T));
+  if (scratch_bytes < p.total || scratch == nullptr) {
+    set_error("%s: scratch too small (%zu < %zu bytes)", who, scratch_bytes, p.total);
+    return AUXSSM_ERR_SCRATCH;
+  }
+  LogpdfArgs<T> a;
+  a.d = *d;
+  a.which = which;
+  a.ys = ys; a.xs = xs; a.ell = ell; a.m0 = m0; a.P0 = P0; a.Fs = Fs; a.Qs = Qs; a.bs = bs; a.Hs = Hs; a.Rs = Rs;
+  a.cs = cs; a.out = out;
+  a.partial = static_cast<T*>(scratch);
+  a.n_tiles = p.n_tiles;
+  a.tile_len = p.tile_len;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int dmax = d->dx > d->dy ? d->dx : d->dy;
+  switch (padded_dim(dmax)) {
+    case 4: rc = launch_logpdf<T, 4>(st, a); break;
+    case 8: rc = launch_logpdf<T, 8>(st, a); break;
+    case 16: rc = launch_logpdf<T, 16>(st, a); break;
+    case 32: rc = launch_logpdf<T, 32>(st, a); break;
+    case 64: rc = launch_logpdf<T, 64>(st, a); break;
+    default: set_error("%s: unsupported dimension %d", who, dmax); return AUXSSM_ERR_UNSUPPORTED;
+  }
+  if (rc) return rc;
+  logpdf_reduce_kernel<T><<<(d->n_chains + 127) / 128, 128, 0, st>>>(
+      a.partial, ell, out, d->n_chains, d->n_batch * p.n_tiles, (which & AUXSSM_LOGPDF_MINUS_ELL) ? 1 : 0);
+  AUXSSM_CHECK_LAUNCH("auxssm_lgssm_logpdf (reduce)");
+  return AUXSSM_OK;
+}
+
+}  // namespace auxssm
+
+extern "C" __attribute__((visibility("default"))) size_t auxssm_lgssm_logpdf_scratch_bytes(const auxssm_lgssm_desc* desc, int32_t elem_size) {
+  if (auxssm::check_desc(desc, "auxssm_lgssm_logpdf_scratch_bytes")) return 0;
+  return auxssm::make_logpdf_plan(desc, (size_t)elem_size).total;
+}
+extern "C" __attribute__((visibility("default"))) int32_t auxssm_lgssm_logpdf_f32(void* stream, const auxssm_lgssm_desc* desc, uint32_t which,
+                                           const float* ys, const float* xs, const float* ell, const float* m0,
+                                           const float* P0, const float* Fs, const float* Qs, const float* bs,
+                                           const float* Hs, const float* Rs, const float* cs, float* out,
+                                           void* scratch, size_t scratch_bytes) {
+  return auxssm::logpdf_entry<float>(stream, desc, which, ys, xs, ell, m0, P0, Fs, Qs, bs, Hs, Rs, cs, out, scratch,
+                                     scratch_bytes);
+}
+extern "C" __attribute__((visibility("default"))) int32_t auxssm_lgssm_logpdf_f64(void* stream, const auxssm_lgssm_desc* desc, uint32_t which,
+                                           const double* ys, const double* xs, const double* ell, const double* m0,
+                                           const double* P0, const double* Fs, const double* Qs, const double* bs,
+                                           const double* Hs, const double* Rs, const double* cs, double* out,
+                                           void* scratch, size_t scratch_bytes) {
+  return auxssm::logpdf_entry<double>(stream, desc, which, ys, xs, ell, m0, P0, Fs, Qs, bs, Hs, Rs, cs, out, scratch,
+                                      scratch_bytes);
+}

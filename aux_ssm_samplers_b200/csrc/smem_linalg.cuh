@@ -1,0 +1,373 @@
+// CTA-cooperative dense linear algebra on small matrices held in shared memory.
+//
+// One CTA owns one (chain, inner-batch, time-chunk) unit; all d x d operands of a
+// Kalman step / scan-element combine live in shared memory in a padded row-major
+// layout with a compile-time leading dimension Tile<D>::LD, where D is max(dx, dy)
+// rounded up to {4, 8, 16, 32, 64}.  INVARIANT: every matrix buffer is zero outside
+// its logical [rows x cols] block, so products may run over whole register tiles.
+//
+// The product primitive is  C = X^T Y  with BOTH operands "k-major" (row k of X and of
+// Y is contiguous): each thread owns a TM x TN register tile and reads its X/Y slices
+// with one vector LDS each per k.  Every product on the hot path is phrased in that
+// form (transposed copies of F and H are staged once; P, Q, R, S, C, J are symmetric).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace auxssm {
+
+template <int D> struct Tile;
+template <> struct Tile<4>  { static constexpr int LD = 4,  NT = 32,  TM = 1, TN = 1; };
+template <> struct Tile<8>  { static constexpr int LD = 12, NT = 32,  TM = 1, TN = 2; };
+template <> struct Tile<16> { static constexpr int LD = 20, NT = 32,  TM = 2, TN = 4; };
+template <> struct Tile<32> { static constexpr int LD = 36, NT = 64,  TM = 4, TN = 4; };
+template <> struct Tile<64> { static constexpr int LD = 68, NT = 256, TM = 4, TN = 4; };
+
+template <int D> __device__ __forceinline__ void cta_sync() {
+  if (Tile<D>::NT == 32) __syncwarp(); else __syncthreads();
+}
+
+template <typename T, int N> struct alignas((sizeof(T) * N > 16) ? 16 : sizeof(T) * N) Vec { T v[N]; };
+
+template <typename T, int N> __device__ __forceinline__ void ldv(T (&dst)[N], const T* p) {
+  Vec<T, N> t = *reinterpret_cast<const Vec<T, N>*>(p);
+#pragma unroll
+  for (int i = 0; i < N; ++i) dst[i] = t.v[i];
+}
+template <typename T, int N> __device__ __forceinline__ void stv(T* p, const T (&src)[N]) {
+  Vec<T, N> t;
+#pragma unroll
+  for (int i = 0; i < N; ++i) t.v[i] = src[i];
+  *reinterpret_cast<Vec<T, N>*>(p) = t;
+}
+
+template <typename T> __device__ __forceinline__ T fma_(T a, T b, T c);
+template <> __device__ __forceinline__ float fma_<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> __device__ __forceinline__ double fma_<double>(double a, double b, double c) { return fma(a, b, c); }
+
+template <typename T> __device__ __forceinline__ bool finite_(T x) { return isfinite(x); }
+
+// MODE 0: C = X^T Y ; MODE 1: C = E + X^T Y ; MODE 2: C = E - X^T Y.   K = inner extent.
+// X, Y, C, E are D x LD shared buffers; C may alias E but must not alias X or Y.
+template <typename T, int D, int MODE>
+__device__ __forceinline__ void mm_tn(const T* __restrict__ X, const T* __restrict__ Y, T* C, const T* E, int K) {
+  using Tl = Tile<D>;
+  constexpr int LD = Tl::LD, TM = Tl::TM, TN = Tl::TN, NT = Tl::NT;
+  constexpr int TX = D / TN, TILES = (D / TM) * TX;
+  cta_sync<D>();
+  for (int tile = threadIdx.x; tile < TILES; tile += NT) {
+    const int ty = tile / TX, tx = tile % TX;
+    T acc[TM][TN];
+#pragma unroll
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+      for (int c = 0; c < TN; ++c) acc[r][c] = T(0);
+    const T* xp = X + ty * TM;
+    const T* yp = Y + tx * TN;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      T xa[TM], yb[TN];
+      ldv<T, TM>(xa, xp + k * LD);
+      ldv<T, TN>(yb, yp + k * LD);
+#pragma unroll
+      for (int r = 0; r < TM; ++r)
+#pragma unroll
+        for (int c = 0; c < TN; ++c) acc[r][c] = fma_(xa[r], yb[c], acc[r][c]);
+    }
+#pragma unroll
+    for (int r = 0; r < TM; ++r) {
+      T* cp = C + (ty * TM + r) * LD + tx * TN;
+      T out[TN];
+      if (MODE == 0) {
+#pragma unroll
+        for (int c = 0; c < TN; ++c) out[c] = acc[r][c];
+      } else {
+        T e[TN];
+        ldv<T, TN>(e, E + (ty * TM + r) * LD + tx * TN);
+#pragma unroll
+        for (int c = 0; c < TN; ++c) out[c] = (MODE == 1) ? e[c] + acc[r][c] : e[c] - acc[r][c];
+      }
+      stv<T, TN>(cp, out);
+    }
+  }
+  cta_sync<D>();
+}
+
+// y[0..M) (op)= A^T x  where A is k-major: y[i] = sum_k A[k][i] x[k], k < K.  MODE as mm_tn with e.
+template <typename T, int D, int MODE>
+__device__ __forceinline__ void mv_tn(const T* A, const T* x, T* y, const T* e, int K, int M) {
+  constexpr int LD = Tile<D>::LD;
+  cta_sync<D>();
+  T acc = T(0);
+  const int i = threadIdx.x;
+  if (i < M) {
+    for (int k = 0; k < K; ++k) acc = fma_(A[k * LD + i], x[k], acc);
+  }
+  T out = acc;
+  if (MODE == 1 && i < M) out = e[i] + acc;
+  if (MODE == 2 && i < M) out = e[i] - acc;
+  cta_sync<D>();  // y may alias x or e
+  if (i < M) y[i] = out;
+  cta_sync<D>();
+}
+
+// y = A x with A row-major (non k-major): y[i] = sum_k A[i][k] x[k].
+template <typename T, int D, int MODE>
+__device__ __forceinline__ void mv_nn(const T* A, const T* x, T* y, const T* e, int M, int K) {
+  constexpr int LD = Tile<D>::LD;
+  cta_sync<D>();
+  T acc = T(0);
+  const int i = threadIdx.x;
+  if (i < M) {
+    for (int k = 0; k < K; ++k) acc = fma_(A[i * LD + k], x[k], acc);
+  }
+  T out = acc;
+  if (MODE == 1 && i < M) out = e[i] + acc;
+  if (MODE == 2 && i < M) out = e[i] - acc;
+  cta_sync<D>();
+  if (i < M) y[i] = out;
+  cta_sync<D>();
+}
+
+template <typename T, int D> __device__ __forceinline__ void zero_mat(T* A) {
+  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  for (int i = threadIdx.x; i < D * LD; i += NT) A[i] = T(0);
+}
+
+// dst = src^T: dst[j][i] = src[i][j] for i < rows, j < cols, zero elsewhere (whole D x D tile).
+template <typename T, int D> __device__ __forceinline__ void transpose_to(const T* src, T* dst, int rows, int cols) {
+  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  cta_sync<D>();
+  for (int e = threadIdx.x; e < D * D; e += NT) {
+    const int i = e / D, j = e % D;  // dst[i][j] = src[j][i]
+    dst[i * LD + j] = (j < rows && i < cols) ? src[j * LD + i] : T(0);
+  }
+  cta_sync<D>();
+}
+
+// A = 0.5 (A + A^T) on the n x n block.
+template <typename T, int D> __device__ __forceinline__ void symmetrize(T* A, int n) {
+  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  cta_sync<D>();
+  for (int e = threadIdx.x; e < n * n; e += NT) {
+    const int i = e / n, j = e % n;
+    if (i < j) {
+      const T v = T(0.5) * (A[i * LD + j] + A[j * LD + i]);
+      A[i * LD + j] = v;
+      A[j * LD + i] = v;
+    }
+  }
+  cta_sync<D>();
+}
+
+// Copy the logical block [rows x cols] between shared buffers.
+template <typename T, int D> __device__ __forceinline__ void copy_mat(const T* src, T* dst, int rows, int cols) {
+  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  cta_sync<D>();
+  for (int e = threadIdx.x; e < rows * cols; e += NT) {
+    const int i = e / cols, j = e % cols;
+    dst[i * LD + j] = src[i * LD + j];
+  }
+  cta_sync<D>();
+}
+
+// Load a [rows x cols] row-major contiguous global block into shared (optionally transposed).
+template <typename T, int D, bool TRANS>
+__device__ __forceinline__ void load_mat(const T* __restrict__ g, T* s, int rows, int cols) {
+  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  for (int e = threadIdx.x; e < rows * cols; e += NT) {
+    const int i = e / cols, j = e % cols;
+    const T v = g[e];
+    if (TRANS) s[j * LD + i] = v; else s[i * LD + j] = v;
+  }
+}
+template <typename T, int D>
+__device__ __forceinline__ void store_mat(T* __restrict__ g, const T* s, int rows, int cols) {
+  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  for (int e = threadIdx.x; e < rows * cols; e += NT) {
+    const int i = e / cols, j = e % cols;
+    g[e] = s[i * LD + j];
+  }
+}
+template <typename T, int D>
+__device__ __forceinline__ void store_mat_t(T* __restrict__ g, const T* s, int rows, int cols) {
+  // global [rows x cols] <- transpose of shared [cols x rows]
+  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  for (int e = threadIdx.x; e < rows * cols; e += NT) {
+    const int i = e / cols, j = e % cols;
+    g[e] = s[j * LD + i];
+  }
+}
+
+// In-place lower Cholesky of the n x n block (thread i owns row i).  `dg` (>= n entries) receives
+// the diagonal of L; it is also written back to the diagonal.  Non-positive pivots give NaN.
+template <typename T, int D> __device__ __forceinline__ void chol_inplace(T* A, T* dg, int n) {
+  constexpr int LD = Tile<D>::LD;
+  const int i = threadIdx.x;
+  for (int k = 0; k < n; ++k) {
+    cta_sync<D>();
+    const T lkk = sqrt(A[k * LD + k]);
+    T lik = T(0);
+    if (i == k) dg[k] = lkk;
+    if (i > k && i < n) {
+      lik = A[i * LD + k] / lkk;
+      A[i * LD + k] = lik;
+    }
+    cta_sync<D>();
+    if (i > k && i < n) {
+      for (int j = k + 1; j <= i; ++j) A[i * LD + j] = fma_(-lik, A[j * LD + k], A[i * LD + j]);
+    }
+  }
+  cta_sync<D>();
+  if (i < n) {
+    A[i * LD + i] = dg[i];
+    for (int j = i + 1; j < n; ++j) A[i * LD + j] = T(0);
+  }
+  cta_sync<D>();
+}
+
+// Z = L^{-1} B in place for the n x m block B (thread j owns column j).  `bvec` (may be null) is
+// one extra right-hand-side vector of length n handled by thread m (requires NT > m).
+template <typename T, int D> __device__ __forceinline__ void fwd_solve(const T* L, T* B, T* bvec, int n, int m) {
+  constexpr int LD = Tile<D>::LD;
+  cta_sync<D>();
+  const int j = threadIdx.x;
+  if (j < m) {
+    for (int i = 0; i < n; ++i) {
+      T acc = B[i * LD + j];
+      for (int k = 0; k < i; ++k) acc = fma_(-L[i * LD + k], B[k * LD + j], acc);
+      B[i * LD + j] = acc / L[i * LD + i];
+    }
+  } else if (j == m && bvec != nullptr) {
+    for (int i = 0; i < n; ++i) {
+      T acc = bvec[i];
+      for (int k = 0; k < i; ++k) acc = fma_(-L[i * LD + k], bvec[k], acc);
+      bvec[i] = acc / L[i * LD + i];
+    }
+  }
+  cta_sync<D>();
+}
+
+// X = (L L^T)^{-1} B in place (n x m block, thread j owns column j).
+template <typename T, int D> __device__ __forceinline__ void cho_solve_cols(const T* L, T* B, int n, int m) {
+  constexpr int LD = Tile<D>::LD;
+  cta_sync<D>();
+  const int j = threadIdx.x;
+  if (j < m) {
+    for (int i = 0; i < n; ++i) {
+      T acc = B[i * LD + j];
+      for (int k = 0; k < i; ++k) acc = fma_(-L[i * LD + k], B[k * LD + j], acc);
+      B[i * LD + j] = acc / L[i * LD + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      T acc = B[i * LD + j];
+      for (int k = i + 1; k < n; ++k) acc = fma_(-L[k * LD + i], B[k * LD + j], acc);
+      B[i * LD + j] = acc / L[i * LD + i];
+    }
+  }
+  cta_sync<D>();
+}
+
+// LU with partial pivoting of the n x n block, in place (packed L\U in pivot order), thread i owns
+// row i.  perm[p] = original row placed at position p.  `red` needs >= 2*NT/32 + 2 words of T and
+// `ired` >= NT/32 + 1 ints (shared).  Rows are physically swapped, LAPACK style.
+template <typename T, int D>
+__device__ __forceinline__ void lu_inplace(T* A, int* perm, T* red, int* ired, int n) {
+  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT, NW = NT / 32;
+  const int i = threadIdx.x, lane = i & 31, w = i >> 5;
+  if (i < n) perm[i] = i;
+  for (int k = 0; k < n; ++k) {
+    cta_sync<D>();
+    // argmax |A[r][k]|, r >= k
+    T v = (i >= k && i < n) ? fabs(A[i * LD + k]) : T(-1);
+    if (i >= k && i < n && !(v == v)) v = T(INFINITY);  // NaN pivots first, so they propagate like LAPACK
+    int r = i;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const T ov = __shfl_xor_sync(0xffffffffu, v, off);
+      const int orr = __shfl_xor_sync(0xffffffffu, r, off);
+      if (ov > v || (ov == v && orr < r)) { v = ov; r = orr; }
+    }
+    if (NW > 1) {
+      if (lane == 0) { red[w] = v; ired[w] = r; }
+      __syncthreads();
+      v = red[0]; r = ired[0];
+      for (int q = 1; q < NW; ++q) {
+        if (red[q] > v || (red[q] == v && ired[q] < r)) { v = red[q]; r = ired[q]; }
+      }
+      __syncthreads();
+    }
+    const int p = r;  // pivot row (uniform)
+    if (p != k) {
+      for (int j = i; j < n; j += NT) {
+        const T t = A[k * LD + j];
+        A[k * LD + j] = A[p * LD + j];
+        A[p * LD + j] = t;
+      }
+      if (i == 0) { const int t = perm[k]; perm[k] = perm[p]; perm[p] = t; }
+    }
+    cta_sync<D>();
+    const T piv = A[k * LD + k];
+    T l = T(0);
+    if (i > k && i < n) {
+      l = A[i * LD + k] / piv;
+    }
+    cta_sync<D>();
+    if (i > k && i < n) {
+      A[i * LD + k] = l;
+      for (int j = k + 1; j < n; ++j) A[i * LD + j] = fma_(-l, A[k * LD + j], A[i * LD + j]);
+    }
+  }
+  cta_sync<D>();
+}
+
+// Solve (P^T L U) X = B for the n x m block B, result written to X (X must not alias B).
+// Thread j owns column j.  `bvec`/`xvec`: optional extra vector RHS handled by thread m.
+template <typename T, int D>
+__device__ __forceinline__ void lu_solve(const T* LU, const int* perm, const T* B, T* X, const T* bvec, T* xvec,
+                                         int n, int m) {
+  constexpr int LD = Tile<D>::LD;
+  cta_sync<D>();
+  const int j = threadIdx.x;
+  if (j < m) {
+    for (int i = 0; i < n; ++i) {
+      T acc = B[perm[i] * LD + j];
+      for (int k = 0; k < i; ++k) acc = fma_(-LU[i * LD + k], X[k * LD + j], acc);
+      X[i * LD + j] = acc;
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      T acc = X[i * LD + j];
+      for (int k = i + 1; k < n; ++k) acc = fma_(-LU[i * LD + k], X[k * LD + j], acc);
+      X[i * LD + j] = acc / LU[i * LD + i];
+    }
+  } else if (j == m && bvec != nullptr) {
+    for (int i = 0; i < n; ++i) {
+      T acc = bvec[perm[i]];
+      for (int k = 0; k < i; ++k) acc = fma_(-LU[i * LD + k], xvec[k], acc);
+      xvec[i] = acc;
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      T acc = xvec[i];
+      for (int k = i + 1; k < n; ++k) acc = fma_(-LU[i * LD + k], xvec[k], acc);
+      xvec[i] = acc / LU[i * LD + i];
+    }
+  }
+  cta_sync<D>();
+}
+
+// Block-wide sum of one value per thread; result valid in every thread.  `red` >= NT/32 words.
+template <typename T, int D> __device__ __forceinline__ T cta_sum(T v, T* red) {
+  constexpr int NW = Tile<D>::NT / 32;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if (NW == 1) return v;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T s = T(0);
+  for (int q = 0; q < NW; ++q) s += red[q];
+  return s;
+}
+
+}  // namespace auxssm
