@@ -32,9 +32,10 @@ def chol(a):
     return L
 
 
-def solve_lower(L, b):
-    """Solve L x = b for lower-triangular L; b is (..., n) or (..., n, m)."""
-    vec = b.ndim == L.ndim - 1
+def solve_lower(L, b, vec=None):
+    """Solve L x = b for lower-triangular L; b is (..., n) [vec=True] or (..., n, m)."""
+    if vec is None:
+        vec = b.ndim == L.ndim - 1
     if vec:
         b = b[..., None]
     n = L.shape[-1]
@@ -94,7 +95,7 @@ def mvn_logpdf(x, m, chol_):
     dim = np.sum(np.isfinite(diag), axis=-1)
     clip = np.where(np.isfinite(chol_), chol_, np.inf)
     with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
-        y = solve_lower(clip, x - m)
+        y = solve_lower(clip, x - m, vec=True)
         const = tril_log_det(chol_) + 0.5 * dim * LOG_2PI
         return -0.5 * np.sum(y * y, axis=-1) - const
 
