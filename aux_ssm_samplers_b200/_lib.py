@@ -43,6 +43,7 @@ _DESC = ctypes.POINTER(LgssmDesc)
 _SIGNATURES = {
     "auxssm_last_error": (ctypes.c_char_p, []),
     "auxssm_version": (_I32, []),
+    "auxssm_launch_count": (ctypes.c_int64, []),
     "auxssm_kalman_filter_scratch_bytes": (_SZ, [_DESC, _I32]),
     "auxssm_kalman_filter_{s}": (_I32, [_P, _DESC] + [_P] * 12 + [_P, _SZ]),
     "auxssm_kalman_sample_scratch_bytes": (_SZ, [_DESC, _I32]),
@@ -101,6 +102,58 @@ def check(rc, what):
     if rc != 0:
         msg = lib().auxssm_last_error().decode("utf-8", "replace")
         raise AuxssmError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+class Profiler:
+    """Brackets every C-ABI call with CUDA events on the current stream (bench.py's per-kernel timing)."""
+
+    def __init__(self):
+        self.records = []  # (name, start_event, end_event)
+        self._open = None
+
+    def begin(self, name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._open = (name, ev)
+
+    def end(self, name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.records.append((self._open[0], self._open[1], ev))
+        self._open = None
+
+    def summary(self):
+        """name -> (calls, total_ms); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, a, b in self.records:
+            n, ms = out.get(name, (0, 0.0))
+            out[name] = (n + 1, ms + a.elapsed_time(b))
+        return out
+
+
+_profiler = None
+
+
+def set_profiler(p):
+    global _profiler
+    _profiler = p
+
+
+def call(name, *args):
+    """Invoke one C-ABI entry point; raises AuxssmError on a non-zero status."""
+    fn = getattr(lib(), name)
+    p = _profiler
+    if p is not None:
+        p.begin(name)
+    rc = fn(*args)
+    if p is not None:
+        p.end(name)
+    check(rc, name)
+
+
+def launch_count():
+    """Cumulative number of CUDA kernels libauxssm.so has launched in this process."""
+    return int(lib().auxssm_launch_count())
 
 
 def stream_ptr(device):

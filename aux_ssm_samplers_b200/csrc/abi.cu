@@ -1,11 +1,17 @@
 // libauxssm: error channel, descriptor validation and launch policy shared by all entry points.
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace auxssm {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -70,3 +76,4 @@ int check_desc(const auxssm_lgssm_desc* d, const char* who) {
 
 extern "C" __attribute__((visibility("default"))) const char* auxssm_last_error(void) { return auxssm::g_err; }
 extern "C" __attribute__((visibility("default"))) int32_t auxssm_version(void) { return AUXSSM_VERSION; }
+extern "C" __attribute__((visibility("default"))) int64_t auxssm_launch_count(void) { return auxssm::launches(); }

@@ -10,6 +10,7 @@
 namespace auxssm {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 inline int padded_dim(int d) {
   if (d <= 4) return 4;
@@ -40,6 +41,7 @@ __host__ __device__ inline int64_t unit_off(const auxssm_stride& s, int c, int b
       auxssm::set_error("%s: CUDA launch failed: %s", who, cudaGetErrorString(e__)); \
       return AUXSSM_ERR_LAUNCH;                                               \
     }                                                                         \
+    auxssm::count_launch();                                                   \
   } while (0)
 
 template <typename K> inline int ensure_smem(K kernel, size_t bytes, const char* who) {

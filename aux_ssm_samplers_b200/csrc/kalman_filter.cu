@@ -193,8 +193,10 @@ template <typename T, int D> __device__ __forceinline__ void store_state(const F
 
 template <typename T, int D> __device__ __forceinline__ StepBuf<T, D> carve_step(Carve<T, D>& cv, bool hid) {
   StepBuf<T, D> s;
-  s.P = cv.mat(); s.W = cv.mat(); s.S = cv.mat(); s.U = cv.mat();
+  s.P = cv.mat(); s.W = cv.mat(); s.S = cv.mat();
   s.Ft = cv.mat(); s.Q = cv.mat(); s.R = cv.mat();
+  // with H = I the update never needs W (P F^T is dead after the predict), so U shares its storage
+  s.U = hid ? s.W : cv.mat();
   s.Ht = hid ? nullptr : cv.mat();
   s.m = cv.vec(); s.bv = cv.vec(); s.y = cv.vec(); s.c = cv.vec(); s.v = cv.vec(); s.dg = cv.vec();
   s.red = cv.vec();
@@ -205,7 +207,7 @@ template <typename T, int D> __device__ __forceinline__ StepBuf<T, D> carve_step
 }
 
 template <int D> __host__ __device__ constexpr size_t step_smem_elems(bool hid) {
-  return (size_t)(hid ? 7 : 8) * D * Tile<D>::LD + 7 * D + D /* mask, generous */ + 16;
+  return (size_t)(hid ? 6 : 8) * D * Tile<D>::LD + 7 * D + D /* mask, generous */ + 16;
 }
 
 // Runs t = t_begin .. t_end-1 of the recursion starting from the state in s (valid for t_begin-1),

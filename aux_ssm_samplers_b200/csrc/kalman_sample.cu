@@ -43,14 +43,16 @@ template <typename T, int D> struct SampBuf {
   T *m, *bv, *eps, *x, *r, *dg, *e, *eagg, *red;
 };
 
-template <int D> __host__ __device__ constexpr size_t samp_smem_elems() {
-  return (size_t)8 * D * Tile<D>::LD + 9 * D + 16;
+// The direct recursion needs 6 matrix buffers; the chunk-aggregate pass one more (the composite map).
+template <int D> __host__ __device__ constexpr size_t samp_smem_elems(bool aggregate) {
+  return (size_t)(aggregate ? 7 : 6) * D * Tile<D>::LD + 9 * D + 16;
 }
 
-template <typename T, int D> __device__ __forceinline__ SampBuf<T, D> carve_samp(SCarve<T, D>& cv) {
+template <typename T, int D> __device__ __forceinline__ SampBuf<T, D> carve_samp(SCarve<T, D>& cv, bool aggregate) {
   SampBuf<T, D> s;
   s.P = cv.mat(); s.W = cv.mat(); s.S = cv.mat(); s.Z = cv.mat(); s.Ft = cv.mat(); s.Q = cv.mat();
-  s.Gagg = cv.mat(); s.Gt = cv.mat();
+  s.Gagg = aggregate ? cv.mat() : nullptr;
+  s.Gt = nullptr;
   s.m = cv.vec(); s.bv = cv.vec(); s.eps = cv.vec(); s.x = cv.vec(); s.r = cv.vec(); s.dg = cv.vec();
   s.e = cv.vec(); s.eagg = cv.vec(); s.red = cv.vec();
   return s;
@@ -116,9 +118,9 @@ __global__ void __launch_bounds__(Tile<D>::NT) sample_recursion_kernel(SampleArg
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SCarve<T, D> cv{reinterpret_cast<T*>(smem_raw)};
   constexpr int NT = Tile<D>::NT, LD = Tile<D>::LD;
-  for (size_t e = threadIdx.x; e < samp_smem_elems<D>(); e += NT) cv.p[e] = T(0);
+  for (size_t e = threadIdx.x; e < samp_smem_elems<D>(false); e += NT) cv.p[e] = T(0);
   __syncthreads();
-  SampBuf<T, D> s = carve_samp<T, D>(cv);
+  SampBuf<T, D> s = carve_samp<T, D>(cv, false);
   const int unit = blockIdx.x;
   const int c = unit / a.d.n_batch, b = unit % a.d.n_batch;
   const int dx = a.d.dx, Tn = a.d.T;
@@ -158,9 +160,9 @@ __global__ void __launch_bounds__(Tile<D>::NT) sample_aggregate_kernel(SampleArg
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SCarve<T, D> cv{reinterpret_cast<T*>(smem_raw)};
   constexpr int NT = Tile<D>::NT, LD = Tile<D>::LD;
-  for (size_t e = threadIdx.x; e < samp_smem_elems<D>(); e += NT) cv.p[e] = T(0);
+  for (size_t e = threadIdx.x; e < samp_smem_elems<D>(true); e += NT) cv.p[e] = T(0);
   __syncthreads();
-  SampBuf<T, D> s = carve_samp<T, D>(cv);
+  SampBuf<T, D> s = carve_samp<T, D>(cv, true);
   const int unit = blockIdx.x, j = blockIdx.y;
   const int c = unit / a.d.n_batch, b = unit % a.d.n_batch;
   const int dx = a.d.dx, Tn = a.d.T;
@@ -291,15 +293,19 @@ static SamplePlan make_sample_plan(const auxssm_lgssm_desc* d, size_t es) {
 template <typename T, int D> static int launch_sample(cudaStream_t st, const SampleArgs<T>& a) {
   const int units = a.d.n_chains * a.d.n_batch;
   constexpr int NT = Tile<D>::NT;
-  const size_t smem = samp_smem_elems<D>() * sizeof(T);
+  const size_t smem = samp_smem_elems<D>(false) * sizeof(T);
   int rc = ensure_smem(sample_recursion_kernel<T, D>, smem, "auxssm_kalman_sample");
   if (rc) return rc;
+  if (a.n_chunks > 1) {
+    rc = ensure_smem(sample_aggregate_kernel<T, D>, samp_smem_elems<D>(true) * sizeof(T),
+                     "auxssm_kalman_sample (parallel)");
+    if (rc) return rc;
+  }
   sample_recursion_kernel<T, D><<<units, NT, smem, st>>>(a);
   AUXSSM_CHECK_LAUNCH("auxssm_kalman_sample (recursion)");
   if (a.n_chunks > 1) {
-    rc = ensure_smem(sample_aggregate_kernel<T, D>, smem, "auxssm_kalman_sample (parallel)");
-    if (rc) return rc;
-    sample_aggregate_kernel<T, D><<<dim3(units, a.n_chunks - 1), NT, smem, st>>>(a);
+    const size_t smem_agg = samp_smem_elems<D>(true) * sizeof(T);
+    sample_aggregate_kernel<T, D><<<dim3(units, a.n_chunks - 1), NT, smem_agg, st>>>(a);
     AUXSSM_CHECK_LAUNCH("auxssm_kalman_sample (aggregate)");
     sample_boundary_kernel<T><<<units, 64, 0, st>>>(a);
     AUXSSM_CHECK_LAUNCH("auxssm_kalman_sample (boundary)");

@@ -192,11 +192,10 @@ def filtering(ys, lgssm, parallel, *, inner_batch=False, time_chunks=0):
     L = _lib.lib()
     nbytes = L.auxssm_kalman_filter_scratch_bytes(d, ys.element_size())
     scratch = _scratch(nbytes, dev)
-    rc = getattr(L, "auxssm_kalman_filter_" + sfx)(
+    _lib.call("auxssm_kalman_filter_" + sfx,
         _lib.stream_ptr(dev), d, _lib.ptr(ysc), _lib.ptr(p["m0"]), _lib.ptr(p["P0"]), _lib.ptr(p["Fs"]),
         _lib.ptr(p["Qs"]), _lib.ptr(p["bs"]), _lib.ptr(p["Hs"]), _lib.ptr(p["Rs"]), _lib.ptr(p["cs"]),
         _lib.ptr(ms), _lib.ptr(Ps), _lib.ptr(ell), _lib.ptr(scratch), scratch.numel())
-    _lib.check(rc, "auxssm_kalman_filter_" + sfx)
     return ms, Ps, (ell if dims.has_chain else ell[0])
 
 
@@ -226,10 +225,9 @@ def sampling(key, ms, Ps, lgssm, parallel, *, inner_batch=False, time_chunks=0):
     _, d.xs = _canon(xs, (dx,), dims.T, dims, "xs")
     L = _lib.lib()
     scratch = _scratch(L.auxssm_kalman_sample_scratch_bytes(d, ms.element_size()), dev)
-    rc = getattr(L, "auxssm_kalman_sample_" + sfx)(
+    _lib.call("auxssm_kalman_sample_" + sfx,
         _lib.stream_ptr(dev), d, _lib.ptr(msc), _lib.ptr(Psc), _lib.ptr(Fs), _lib.ptr(Qs), _lib.ptr(bs),
         _lib.ptr(epsc), _lib.ptr(xs), _lib.ptr(scratch), scratch.numel())
-    _lib.check(rc, "auxssm_kalman_sample_" + sfx)
     return xs
 
 
@@ -255,11 +253,10 @@ def _logpdf(which, ys, xs, ell, lgssm, inner_batch):
     out = torch.empty((dims.C,), dtype=dtype, device=dev)
     L = _lib.lib()
     scratch = _scratch(L.auxssm_lgssm_logpdf_scratch_bytes(d, xs.element_size()), dev)
-    rc = getattr(L, "auxssm_lgssm_logpdf_" + sfx)(
+    _lib.call("auxssm_lgssm_logpdf_" + sfx,
         _lib.stream_ptr(dev), d, which, _lib.ptr(ysc), _lib.ptr(xsc), _lib.ptr(ellc), _lib.ptr(p["m0"]),
         _lib.ptr(p["P0"]), _lib.ptr(p["Fs"]), _lib.ptr(p["Qs"]), _lib.ptr(p["bs"]), _lib.ptr(p["Hs"]),
         _lib.ptr(p["Rs"]), _lib.ptr(p["cs"]), _lib.ptr(out), _lib.ptr(scratch), scratch.numel())
-    _lib.check(rc, "auxssm_lgssm_logpdf_" + sfx)
     return out if dims.has_chain else out[0]
 
 
@@ -271,7 +268,7 @@ def posterior_logpdf(ys, xs, ell, lgssm, *, inner_batch=False):
 def prior_logpdf(xs, lgssm, *, inner_batch=False):
     """log p(xs) (base.py:100-134)."""
     lg = LGSSM(*lgssm)
-    return _logpdf(_lib.LOGPDF_PRIOR, None, xs, None, lg._replace(Rs=None), inner_batch)
+    return _logpdf(_lib.LOGPDF_PRIOR, None, xs, None, lg._replace(Hs=None, Rs=None, cs=None), inner_batch)
 
 
 def log_likelihood(ys, xs, lgssm, *, inner_batch=False):
@@ -288,10 +285,9 @@ def auxiliary_draw(x, normals, delta):
     C = x.shape[0]
     dl = _as_delta(delta, C, x.dtype, dev)
     u = torch.empty_like(x)
-    rc = getattr(_lib.lib(), "auxssm_auxiliary_draw_" + sfx)(
+    _lib.call("auxssm_auxiliary_draw_" + sfx,
         _lib.stream_ptr(dev), C, x.numel() // C, _lib.ptr(x), _lib.ptr(normals), _lib.ptr(dl),
         1 if dl.numel() > 1 else 0, _lib.ptr(u))
-    _lib.check(rc, "auxssm_auxiliary_draw_" + sfx)
     return u
 
 
@@ -315,11 +311,10 @@ def mh_accept(x, x_prop, u, delta, log_lgssm_prop, log_lgssm_rev, log_target_pro
     args = [vec(log_lgssm_prop), vec(log_lgssm_rev), vec(log_target_prop), vec(log_target_rev)]
     un = vec(uniforms)
     uc, xp = u.contiguous(), x_prop.contiguous()
-    rc = getattr(_lib.lib(), "auxssm_kalman_mh_" + sfx)(
+    _lib.call("auxssm_kalman_mh_" + sfx,
         _lib.stream_ptr(dev), C, x.numel() // C, _lib.ptr(dl), 1 if dl.numel() > 1 else 0,
         _lib.ptr(args[0]), _lib.ptr(args[1]), _lib.ptr(args[2]), _lib.ptr(args[3]), _lib.ptr(uc), _lib.ptr(xp),
         _lib.ptr(un), _lib.ptr(x_new), _lib.ptr(accepted), _lib.ptr(alpha))
-    _lib.check(rc, "auxssm_kalman_mh_" + sfx)
     return x_new, accepted.bool(), alpha
 
 

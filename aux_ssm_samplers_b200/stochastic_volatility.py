@@ -41,10 +41,9 @@ def observations_factory(ys, x, u, delta, order):
     else:
         Rs = torch.empty((C, T, d, d), dtype=x.dtype, device=dev)
     ys_stride = 0 if ys.dim() == 2 else T * d
-    rc = getattr(_lib.lib(), "auxssm_sv_obs_factory_" + sfx)(
+    _lib.call("auxssm_sv_obs_factory_" + sfx,
         _lib.stream_ptr(dev), order, C, T, d, _lib.ptr(ys), ys_stride, _lib.ptr(x), _lib.ptr(u), _lib.ptr(dl),
         1 if dl.numel() > 1 else 0, _lib.ptr(aux_ys), _lib.ptr(Rs))
-    _lib.check(rc, "auxssm_sv_obs_factory_" + sfx)
     return aux_ys, None, Rs, None
 
 
@@ -59,9 +58,8 @@ def log_potential(ys, x, out=None):
     if out is None:
         out = torch.empty((C,), dtype=x.dtype, device=dev)
     ys_stride = 0 if ys.dim() == 2 else T * d
-    rc = getattr(_lib.lib(), "auxssm_sv_log_potential_" + sfx)(
+    _lib.call("auxssm_sv_log_potential_" + sfx,
         _lib.stream_ptr(dev), C, T * d, _lib.ptr(ys), ys_stride, _lib.ptr(x), _lib.ptr(out), 1 if acc else 0)
-    _lib.check(rc, "auxssm_sv_log_potential_" + sfx)
     return out
 
 

@@ -75,6 +75,8 @@ typedef struct auxssm_lgssm_desc {
 
 const char* auxssm_last_error(void);
 int32_t auxssm_version(void);
+/* cumulative number of CUDA kernels this library has launched in the calling process */
+int64_t auxssm_launch_count(void);
 
 /* ---- Kalman filter: replaces filtering(ys, lgssm, parallel), filtering.py:18-46 ------------
  * Outputs ms, Ps (strides desc->ms, desc->Ps) and ell[n_chains] (summed over the inner batch,
