@@ -171,7 +171,7 @@ __device__ __forceinline__ T kalman_update(StepBuf<T, D>& s, int dx, int dy, int
     mm_tn<T, D, 1>(s.W, s.Ht, s.S, s.R, dx);          // S = H P H^T + R
   }
   chol_inplace<T, D>(s.S, s.dg, dy);
-  fwd_solve<T, D>(s.S, s.U, s.v, dy, dx);             // U <- Z = L^{-1} U ; v <- L^{-1} (y - yhat)
+  fwd_solve<T, D>(s.S, s.U, s.v, dy, dx, s.dg);             // U <- Z = L^{-1} U ; v <- L^{-1} (y - yhat)
   mm_tn<T, D, 2>(s.U, s.U, s.P, s.P, dy);             // P -= Z^T Z
   mv_tn<T, D, 1>(s.U, s.v, s.m, s.m, dy, dx);         // m += Z^T v
   symmetrize<T, D>(s.P, dx);
@@ -198,8 +198,8 @@ template <typename T, int D> __device__ __forceinline__ StepBuf<T, D> carve_step
   // with H = I the update never needs W (P F^T is dead after the predict), so U shares its storage
   s.U = hid ? s.W : cv.mat();
   s.Ht = hid ? nullptr : cv.mat();
-  s.m = cv.vec(); s.bv = cv.vec(); s.y = cv.vec(); s.c = cv.vec(); s.v = cv.vec(); s.dg = cv.vec();
-  s.red = cv.vec();
+  s.m = cv.vec(); s.bv = cv.vec(); s.y = cv.vec(); s.c = cv.vec(); s.v = cv.vec(); s.red = cv.vec();
+  s.dg = cv.p; cv.p += CholWs<D>::WORDS;
   s.mask = reinterpret_cast<int*>(cv.p);
   cv.p += (D * sizeof(int) + sizeof(T) - 1) / sizeof(T);
   s.h_clean = s.r_clean = s.c_clean = false;
@@ -207,7 +207,7 @@ template <typename T, int D> __device__ __forceinline__ StepBuf<T, D> carve_step
 }
 
 template <int D> __host__ __device__ constexpr size_t step_smem_elems(bool hid) {
-  return (size_t)(hid ? 6 : 8) * D * Tile<D>::LD + 7 * D + D /* mask, generous */ + 16;
+  return (size_t)(hid ? 6 : 8) * D * Tile<D>::LD + 10 * D + D /* mask, generous */ + 16;
 }
 
 // Runs t = t_begin .. t_end-1 of the recursion starting from the state in s (valid for t_begin-1),
@@ -292,7 +292,7 @@ template <typename T, int D> struct ScanBuf {
 };
 
 template <int D> __host__ __device__ constexpr size_t scan_smem_elems() {
-  return (size_t)13 * D * Tile<D>::LD + 6 * D + 7 * D + D + 2 * D /* perm, ired */ + 32;
+  return (size_t)13 * D * Tile<D>::LD + 6 * D + 10 * D + D + 2 * D /* perm, ired */ + 32;
 }
 
 // Element (A, b, C, eta, J) of time step t (t >= 1, not the first element of the scan), with A
@@ -322,8 +322,8 @@ __device__ __forceinline__ void build_element(const FilterArgs<T>& a, int c, int
   mm_tn<T, D, 1>(Ht, Ut, S, S, dx);                                // S = H Q H^T + R
   transpose_to<T, D>(Ut, Z, dx, dy);                               // Z <- U = H Q        (dy x dx)
   chol_inplace<T, D>(S, s.dg, dy);
-  fwd_solve<T, D>(S, Z, s.v, dy, dx);                              // Z = L^{-1} H Q ; v = L^{-1}(y - Hb - c)
-  fwd_solve<T, D>(S, Hp, nullptr, dy, dx);                         // Hp <- Zh = L^{-1} H
+  fwd_solve<T, D>(S, Z, s.v, dy, dx, s.dg);                              // Z = L^{-1} H Q ; v = L^{-1}(y - Hb - c)
+  fwd_solve<T, D>(S, Hp, nullptr, dy, dx, s.dg);                         // Hp <- Zh = L^{-1} H
   mm_tn<T, D, 2>(Z, Z, sc.C2, sc.C2, dy);                          // C = Q - Z^T Z
   mv_tn<T, D, 1>(Z, s.v, sc.b2, sc.b2, dy, dx);                    // b = b + Z^T v
   symmetrize<T, D>(sc.C2, dx);
@@ -381,7 +381,8 @@ template <typename T, int D> __device__ __forceinline__ ScanBuf<T, D> carve_scan
 template <typename T, int D>
 __device__ __forceinline__ void carve_scan_tail(Carve<T, D>& cv, StepBuf<T, D>& s, ScanBuf<T, D>& sc) {
   s.P = s.W = s.S = s.U = s.Ft = s.Q = s.Ht = s.R = nullptr;
-  s.m = cv.vec(); s.bv = cv.vec(); s.y = cv.vec(); s.c = cv.vec(); s.v = cv.vec(); s.dg = cv.vec(); s.red = cv.vec();
+  s.m = cv.vec(); s.bv = cv.vec(); s.y = cv.vec(); s.c = cv.vec(); s.v = cv.vec(); s.red = cv.vec();
+  s.dg = cv.p; cv.p += CholWs<D>::WORDS;
   s.mask = reinterpret_cast<int*>(cv.p);
   cv.p += (D * sizeof(int) + sizeof(T) - 1) / sizeof(T);
   sc.perm = reinterpret_cast<int*>(cv.p);

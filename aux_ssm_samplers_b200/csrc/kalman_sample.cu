@@ -45,7 +45,7 @@ template <typename T, int D> struct SampBuf {
 
 // The direct recursion needs 6 matrix buffers; the chunk-aggregate pass one more (the composite map).
 template <int D> __host__ __device__ constexpr size_t samp_smem_elems(bool aggregate) {
-  return (size_t)(aggregate ? 7 : 6) * D * Tile<D>::LD + 9 * D + 16;
+  return (size_t)(aggregate ? 7 : 6) * D * Tile<D>::LD + 12 * D + 16;
 }
 
 template <typename T, int D> __device__ __forceinline__ SampBuf<T, D> carve_samp(SCarve<T, D>& cv, bool aggregate) {
@@ -53,8 +53,9 @@ template <typename T, int D> __device__ __forceinline__ SampBuf<T, D> carve_samp
   s.P = cv.mat(); s.W = cv.mat(); s.S = cv.mat(); s.Z = cv.mat(); s.Ft = cv.mat(); s.Q = cv.mat();
   s.Gagg = aggregate ? cv.mat() : nullptr;
   s.Gt = nullptr;
-  s.m = cv.vec(); s.bv = cv.vec(); s.eps = cv.vec(); s.x = cv.vec(); s.r = cv.vec(); s.dg = cv.vec();
+  s.m = cv.vec(); s.bv = cv.vec(); s.eps = cv.vec(); s.x = cv.vec(); s.r = cv.vec();
   s.e = cv.vec(); s.eagg = cv.vec(); s.red = cv.vec();
+  s.dg = cv.p; cv.p += CholWs<D>::WORDS;
   return s;
 }
 
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(Tile<D>::NT) sample_recursion_kernel(SampleArg
     mv_tn<T, D, 1>(s.Ft, s.m, s.r, s.bv, dx, dx);  // r = F m + b
     if (threadIdx.x < dx) s.r[threadIdx.x] = s.x[threadIdx.x] - s.r[threadIdx.x];  // x_{t+1} - F m - b
     chol_inplace<T, D>(s.S, s.dg, dx);
-    fwd_solve<T, D>(s.S, s.Z, s.r, dx, dx);        // Zs = Ls^{-1} F P ; r <- Ls^{-1} r
+    fwd_solve<T, D>(s.S, s.Z, s.r, dx, dx, s.dg);        // Zs = Ls^{-1} F P ; r <- Ls^{-1} r
     mm_tn<T, D, 2>(s.Z, s.Z, s.P, s.P, dx);        // Sigma = P - Zs^T Zs
     symmetrize<T, D>(s.P, dx);
     chol_nan_to_zero<T, D>(s.P, s.dg, dx);         // L = chol(Sigma), NaN -> 0
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(Tile<D>::NT) sample_aggregate_kernel(SampleArg
     mm_tn<T, D, 0>(s.Ft, s.P, s.Z, nullptr, dx);
     mv_tn<T, D, 1>(s.Ft, s.m, s.r, s.bv, dx, dx);  // r = F m + b
     chol_inplace<T, D>(s.S, s.dg, dx);
-    fwd_solve<T, D>(s.S, s.Z, nullptr, dx, dx);    // Zs
+    fwd_solve<T, D>(s.S, s.Z, nullptr, dx, dx, s.dg);    // Zs
     mm_tn<T, D, 2>(s.Z, s.Z, s.P, s.P, dx);        // Sigma
     symmetrize<T, D>(s.P, dx);
     // G^T = Ls^{-T} Zs : back substitution, thread q owns column q of Z

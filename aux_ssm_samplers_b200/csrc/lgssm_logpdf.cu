@@ -26,9 +26,10 @@ template <typename T> __device__ __forceinline__ T half_log_2pi_() { return T(0.
 
 // log N(r; 0, L L^T) for the residual in `r` (overwritten), mvn/base.py:16-58: non-finite diagonal
 // entries of L are dropped from the dimension count and the log-determinant.  Uniform result.
-template <typename T, int D> __device__ __forceinline__ T gauss_logpdf(const T* L, T* r, T* red, int n) {
+template <typename T, int D>
+__device__ __forceinline__ T gauss_logpdf(const T* L, T* r, T* red, int n, const T* dg) {
   constexpr int LD = Tile<D>::LD;
-  fwd_solve<T, D>(L, nullptr, r, n, 0);
+  fwd_solve<T, D>(L, nullptr, r, n, 0, dg);
   T part = T(0);
   const int i = threadIdx.x;
   if (i < n) {
@@ -39,7 +40,7 @@ template <typename T, int D> __device__ __forceinline__ T gauss_logpdf(const T* 
 }
 
 template <int D> __host__ __device__ constexpr size_t logpdf_smem_elems() {
-  return (size_t)4 * D * Tile<D>::LD + 8 * D + 16;
+  return (size_t)4 * D * Tile<D>::LD + 7 * D + 2 * CholWs<D>::WORDS + 16;
 }
 
 template <typename T, int D>
@@ -59,8 +60,9 @@ __global__ void __launch_bounds__(Tile<D>::NT) lgssm_logpdf_kernel(LogpdfArgs<T>
   T* bv = p; p += D;
   T* cv = p; p += D;
   T* yv = p; p += D;
-  T* dg = p; p += D;
   T* red = p; p += D;
+  T* dgQ = p; p += CholWs<D>::WORDS;
+  T* dgR = p; p += CholWs<D>::WORDS;
   const int unit = blockIdx.x, tile = blockIdx.y;
   const int c = unit / a.d.n_batch, b = unit % a.d.n_batch;
   const int dx = a.d.dx, dy = a.d.dy, Tn = a.d.T;
@@ -84,8 +86,8 @@ __global__ void __launch_bounds__(Tile<D>::NT) lgssm_logpdf_kernel(LogpdfArgs<T>
       if (t == 0) {
         load_mat<T, D, false>(a.P0 + unit_off(a.d.P0, c, b), LQ, dx, dx);
         if (i < dx) r[i] = xcur[i] - a.m0[unit_off(a.d.m0, c, b) + i];
-        chol_inplace<T, D>(LQ, dg, dx);
-        T term = gauss_logpdf<T, D>(LQ, r, red, dx);
+        chol_inplace<T, D>(LQ, dgQ, dx);
+        T term = gauss_logpdf<T, D>(LQ, r, red, dx, dgQ);
         if (!(term == term)) term = T(0);
         total += term;
         first_dyn = true;  // LQ now holds chol(P0): force a reload of Q below
@@ -99,12 +101,12 @@ __global__ void __launch_bounds__(Tile<D>::NT) lgssm_logpdf_kernel(LogpdfArgs<T>
         if (first_dyn || a.d.Qs.time != 0) {
           cta_sync<D>();
           load_mat<T, D, false>(a.Qs + unit_off(a.d.Qs, c, b) + (int64_t)tm1 * a.d.Qs.time, LQ, dx, dx);
-          chol_inplace<T, D>(LQ, dg, dx);
+          chol_inplace<T, D>(LQ, dgQ, dx);
         }
         first_dyn = false;
         mv_tn<T, D, 1>(Ft, xprev, r, bv, dx, dx);  // r = F x_{t-1} + b
         if (i < dx) r[i] = xcur[i] - r[i];
-        T term = gauss_logpdf<T, D>(LQ, r, red, dx);
+        T term = gauss_logpdf<T, D>(LQ, r, red, dx, dgQ);
         if (!(term == term)) term = T(0);
         total += term;
       }
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(Tile<D>::NT) lgssm_logpdf_kernel(LogpdfArgs<T>
       if (first_obs || a.d.Rs.time != 0) {
         cta_sync<D>();
         load_mat<T, D, false>(a.Rs + unit_off(a.d.Rs, c, b) + (int64_t)t * a.d.Rs.time, LR, dy, dy);
-        chol_inplace<T, D>(LR, dg, dy);
+        chol_inplace<T, D>(LR, dgR, dy);
       }
       first_obs = false;
       if (i < dy) yv[i] = a.ys[unit_off(a.d.ys, c, b) + (int64_t)t * a.d.ys.time + i];
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(Tile<D>::NT) lgssm_logpdf_kernel(LogpdfArgs<T>
         mv_tn<T, D, 1>(Ht, xcur, r, cv, dx, dy);  // r = H x + c
         if (i < dy) r[i] = yv[i] - r[i];
       }
-      T term = gauss_logpdf<T, D>(LR, r, red, dy);
+      T term = gauss_logpdf<T, D>(LR, r, red, dy, dgR);
       if (!(term == term)) term = T(0);
       total += term;
     }

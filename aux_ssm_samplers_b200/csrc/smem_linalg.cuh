@@ -200,9 +200,117 @@ __device__ __forceinline__ void store_mat_t(T* __restrict__ g, const T* s, int r
   }
 }
 
+// 1 / sqrt(x) and sqrt(x) for a Cholesky pivot.  fp32: MUFU.RSQ + one Newton step (full fp32 accuracy,
+// ~35 cycles instead of sqrt + divide on the serial critical path); NaN for x < 0, like sqrt.
+template <typename T> __device__ __forceinline__ void pivot_(T x, T& l, T& inv);
+template <> __device__ __forceinline__ void pivot_<float>(float x, float& l, float& inv) {
+  float r = rsqrtf(x);
+  r = r * fmaf(-0.5f * x, r * r, 1.5f);
+  inv = r;
+  l = (x == 0.f) ? 0.f : x * r;
+}
+template <> __device__ __forceinline__ void pivot_<double>(double x, double& l, double& inv) {
+  l = sqrt(x);
+  inv = 1.0 / l;
+}
+
+// Register-resident Cholesky for D <= 32: warp 0 only, lane i owns row i in registers; the freshly
+// scaled column k is exchanged through a double-buffered shared vector (one STS + (D-k)/4 broadcast
+// LDS.128 per column, __syncwarp only).  `dg` receives diag(L), `dginv` (optional) its reciprocal.
+// `colbuf` needs 2*D words.  All D x D loops are fully unrolled so the row stays in registers.
+template <typename T, int D>
+__device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n) {
+  constexpr int LD = Tile<D>::LD;
+  constexpr int V = (D >= 4) ? 4 : D;
+  cta_sync<D>();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    T row[D];
+#pragma unroll
+    for (int j = 0; j < D; j += V) {
+      T tmp[V];
+      if (lane < D) ldv<T, V>(tmp, A + lane * LD + j);
+#pragma unroll
+      for (int q = 0; q < V; ++q) row[j + q] = (lane < n) ? tmp[q] : T(0);
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      if (k < n) {
+        const T akk = __shfl_sync(0xffffffffu, row[k], k);
+        T lkk, inv;
+        pivot_<T>(akk, lkk, inv);
+        const T lik = (lane == k) ? lkk : row[k] * inv;
+        row[k] = lik;
+        T* cb = colbuf + (k & 1) * D;
+        if (lane < D) cb[lane] = lik;
+        if (lane == k) {
+          dg[k] = lkk;
+          if (dginv) dginv[k] = inv;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = ((k + 1) / V) * V; j < D; j += V) {
+          T c[V];
+          ldv<T, V>(c, cb + j);
+#pragma unroll
+          for (int q = 0; q < V; ++q)
+            if (j + q > k) row[j + q] = fma_(-lik, c[q], row[j + q]);
+        }
+      }
+    }
+    if (lane < n) {
+#pragma unroll
+      for (int j = 0; j < D; j += V) {
+        T tmp[V];
+#pragma unroll
+        for (int q = 0; q < V; ++q) tmp[q] = (j + q <= lane) ? row[j + q] : T(0);
+        stv<T, V>(A + lane * LD + j, tmp);
+      }
+    }
+  }
+  cta_sync<D>();
+}
+
+// Register-resident forward substitution for D <= 32: thread j owns column j of B (n x m) in
+// registers, rows of L are read as broadcast vector loads, two accumulators per dot product.
+// `dginv` = 1 / diag(L).  Thread m handles the optional extra vector `bvec`.
+template <typename T, int D>
+__device__ __forceinline__ void fwd_solve_reg(const T* L, T* B, T* bvec, const T* dginv, int n, int m) {
+  constexpr int LD = Tile<D>::LD;
+  constexpr int V = (D >= 4) ? 4 : D;
+  cta_sync<D>();
+  const int j = threadIdx.x;
+  const bool is_vec = (j == m) && (bvec != nullptr);
+  if (j < m || is_vec) {
+    T z[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      if (i < n) {
+        T acc0 = is_vec ? bvec[i] : B[i * LD + j];
+        T acc1 = T(0);
+#pragma unroll
+        for (int k = 0; k < ((i + V - 1) / V) * V; k += V) {
+          T l[V];
+          ldv<T, V>(l, L + i * LD + k);
+#pragma unroll
+          for (int q = 0; q < V; ++q) {
+            if (k + q < i) {
+              if ((q & 1) == 0) acc0 = fma_(-l[q], z[k + q], acc0);
+              else acc1 = fma_(-l[q], z[k + q], acc1);
+            }
+          }
+        }
+        z[i] = (acc0 + acc1) * dginv[i];
+        if (is_vec) bvec[i] = z[i]; else B[i * LD + j] = z[i];
+      }
+    }
+  }
+  cta_sync<D>();
+}
+
 // In-place lower Cholesky of the n x n block (thread i owns row i).  `dg` (>= n entries) receives
 // the diagonal of L; it is also written back to the diagonal.  Non-positive pivots give NaN.
-template <typename T, int D> __device__ __forceinline__ void chol_inplace(T* A, T* dg, int n) {
+template <typename T, int D> __device__ __forceinline__ void chol_generic(T* A, T* dg, int n) {
   constexpr int LD = Tile<D>::LD;
   const int i = threadIdx.x;
   for (int k = 0; k < n; ++k) {
@@ -229,7 +337,7 @@ template <typename T, int D> __device__ __forceinline__ void chol_inplace(T* A, 
 
 // Z = L^{-1} B in place for the n x m block B (thread j owns column j).  `bvec` (may be null) is
 // one extra right-hand-side vector of length n handled by thread m (requires NT > m).
-template <typename T, int D> __device__ __forceinline__ void fwd_solve(const T* L, T* B, T* bvec, int n, int m) {
+template <typename T, int D> __device__ __forceinline__ void fwd_solve_generic(const T* L, T* B, T* bvec, int n, int m) {
   constexpr int LD = Tile<D>::LD;
   cta_sync<D>();
   const int j = threadIdx.x;
@@ -247,6 +355,23 @@ template <typename T, int D> __device__ __forceinline__ void fwd_solve(const T* 
     }
   }
   cta_sync<D>();
+}
+
+
+// Workspace convention: a "dg" buffer is 4*D words = [diag(L) | 1/diag(L) | 2*D column exchange].
+template <int D> struct CholWs { static constexpr int WORDS = 4 * D; };
+
+// In-place lower Cholesky of the n x n block; strict upper triangle zeroed; non-PD pivots give NaN.
+template <typename T, int D> __device__ __forceinline__ void chol_inplace(T* A, T* dg, int n) {
+  if constexpr (D <= 32) chol_reg<T, D>(A, dg, dg + D, dg + 2 * D, n);
+  else chol_generic<T, D>(A, dg, n);
+}
+// Z = L^{-1} B in place (n x m block) and optionally bvec <- L^{-1} bvec; `dg` is the workspace the
+// factorisation of L filled.
+template <typename T, int D>
+__device__ __forceinline__ void fwd_solve(const T* L, T* B, T* bvec, int n, int m, const T* dg) {
+  if constexpr (D <= 32) fwd_solve_reg<T, D>(L, B, bvec, dg + D, n, m);
+  else fwd_solve_generic<T, D>(L, B, bvec, n, m);
 }
 
 // X = (L L^T)^{-1} B in place (n x m block, thread j owns column j).
