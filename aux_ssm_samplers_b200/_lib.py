@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libauxssm.so")
 
 AUXSSM_MAX_DIM = 64
 FLAG_H_IDENTITY = 1
+FLAG_R_DIAGONAL = 2
 LOGPDF_PRIOR, LOGPDF_LOGLIK, LOGPDF_MINUS_ELL, LOGPDF_POSTERIOR = 1, 2, 4, 7
 
 
@@ -52,7 +53,7 @@ _SIGNATURES = {
     "auxssm_lgssm_logpdf_{s}": (_I32, [_P, _DESC, _U32] + [_P] * 12 + [_P, _SZ]),
     "auxssm_auxiliary_draw_{s}": (_I32, [_P, _I64, _I64, _P, _P, _P, _I32, _P]),
     "auxssm_kalman_mh_{s}": (_I32, [_P, _I64, _I64, _P, _I32] + [_P] * 10),
-    "auxssm_sv_obs_factory_{s}": (_I32, [_P, _I32, _I64, _I64, _I32, _P, _I64, _P, _P, _P, _I32, _P, _P]),
+    "auxssm_sv_obs_factory_{s}": (_I32, [_P, _I32, _I64, _I64, _I32, _P, _I64, _P, _P, _P, _I32, _P, _P, _I32]),
     "auxssm_sv_log_potential_{s}": (_I32, [_P, _I64, _I64, _P, _I64, _P, _P, _I32]),
 }
 

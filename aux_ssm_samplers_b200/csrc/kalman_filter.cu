@@ -47,6 +47,7 @@ template <typename T, int D> struct Carve {
 template <typename T, int D> struct StepBuf {
   T *P, *W, *S, *U, *Ft, *Q, *Ht, *R;
   T *m, *bv, *y, *c, *v, *dg;
+  T* rd;  // diag(R_t) when AUXSSM_FLAG_R_DIAGONAL
   int* mask;
   T* red;
   bool h_clean, r_clean, c_clean;
@@ -80,7 +81,7 @@ __device__ __forceinline__ void stage_dyn(const FilterArgs<T>& a, int c, int b, 
 template <typename T, int D>
 __device__ __forceinline__ int stage_obs(const FilterArgs<T>& a, int c, int b, int t, bool first, StepBuf<T, D>& s,
                                          T* Hp, bool explicit_identity) {
-  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  constexpr int LD = Tile<D>::LD;
   const int dx = a.d.dx, dy = a.d.dy;
   const bool hid = (a.d.flags & AUXSSM_FLAG_H_IDENTITY) != 0;
   cta_sync<D>();
@@ -96,8 +97,7 @@ __device__ __forceinline__ int stage_obs(const FilterArgs<T>& a, int c, int b, i
   if (first || any_mask || !s.h_clean || (!hid && a.d.Hs.time != 0)) {
     if (hid) {
       if (explicit_identity) {
-        for (int e = threadIdx.x; e < dy * dx; e += NT) {
-          const int i = e / dx, j = e % dx;
+        AUXSSM_FOR_ROWS(i, j, dy, dx) {
           const T v = (i == j && !s.mask[i]) ? T(1) : T(0);
           if (s.Ht) s.Ht[j * LD + i] = v;
           if (Hp) Hp[i * LD + j] = v;
@@ -105,20 +105,28 @@ __device__ __forceinline__ int stage_obs(const FilterArgs<T>& a, int c, int b, i
       }
     } else {
       const T* g = a.Hs + unit_off(a.d.Hs, c, b) + (int64_t)t * a.d.Hs.time;
-      for (int e = threadIdx.x; e < dy * dx; e += NT) {
-        const int i = e / dx, j = e % dx;
-        const T v = s.mask[i] ? T(0) : g[e];
+      AUXSSM_FOR_ROWS(i, j, dy, dx) {
+        const T v = s.mask[i] ? T(0) : g[i * dx + j];
         if (s.Ht) s.Ht[j * LD + i] = v;
         if (Hp) Hp[i * LD + j] = v;
       }
     }
     s.h_clean = !any_mask;
   }
-  if (first || any_mask || !s.r_clean || a.d.Rs.time != 0) {
+  const bool rdiag = (a.d.flags & AUXSSM_FLAG_R_DIAGONAL) != 0;
+  if (rdiag && (first || any_mask || !s.r_clean || a.d.Rs.time != 0)) {
     const T* g = a.Rs + unit_off(a.d.Rs, c, b) + (int64_t)t * a.d.Rs.time;
-    for (int e = threadIdx.x; e < dy * dy; e += NT) {
-      const int i = e / dy, j = e % dy;
-      T v = g[e];
+    if (threadIdx.x < dy) s.rd[threadIdx.x] = s.mask[threadIdx.x] ? T(1) : g[threadIdx.x];
+    if (s.R != nullptr) {
+      cta_sync<D>();
+      AUXSSM_FOR_ROWS(i, j, dy, dy) s.R[i * LD + j] = (i == j) ? s.rd[i] : T(0);
+    }
+    s.r_clean = !any_mask;
+  }
+  if (!rdiag && s.R != nullptr && (first || any_mask || !s.r_clean || a.d.Rs.time != 0)) {
+    const T* g = a.Rs + unit_off(a.d.Rs, c, b) + (int64_t)t * a.d.Rs.time;
+    AUXSSM_FOR_ROWS(i, j, dy, dy) {
+      T v = g[i * dy + j];
       if (s.mask[i] || s.mask[j]) v = (i == j) ? T(1) : T(0);
       s.R[i * LD + j] = v;
     }
@@ -143,24 +151,64 @@ template <typename T, int D> __device__ __forceinline__ void kalman_predict(Step
   mm_tn<T, D, 0>(s.P, s.Ft, s.W, nullptr, dx);   // W = P F^T   (P symmetric)
   mm_tn<T, D, 1>(s.Ft, s.W, s.P, s.Q, dx);       // P = F W + Q
   mv_tn<T, D, 1>(s.Ft, s.m, s.m, s.bv, dx, dx);  // m = F m + b
-  symmetrize<T, D>(s.P, dx);
 }
 
 // Measurement update with the masked observation staged in s; returns the log-likelihood
 // increment (uniform over the CTA).  filtering.py:84-130, with  Z = L^{-1} H P  so that
 // G S G^T = Z^T Z  and  G (y - yhat) = Z^T L^{-1} (y - yhat).
+// R_t kept in registers with the row mapping of AUXSSM_FOR_ROWS (H = I path): element q of thread
+// (warp w, lane) is R[w + (q / CPL) * NW][lane + 32 * (q % CPL)].
+template <int D> struct RowRegs {
+  static constexpr int NW = Tile<D>::NT / 32, RPW = (D + NW - 1) / NW, CPL = (D + 31) / 32, N = RPW * CPL;
+};
+
+template <typename T, int D>
+__device__ __forceinline__ void load_R_regs(const FilterArgs<T>& a, int c, int b, int t, T (&Rr)[RowRegs<D>::N]) {
+  using RR = RowRegs<D>;
+  const int dy = a.d.dy, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* __restrict__ g = a.Rs + unit_off(a.d.Rs, c, b) + (int64_t)t * a.d.Rs.time;
+#pragma unroll
+  for (int qi = 0; qi < RR::RPW; ++qi) {
+    const int i = w + qi * RR::NW;
+#pragma unroll
+    for (int qj = 0; qj < RR::CPL; ++qj) {
+      const int j = lane + 32 * qj;
+      Rr[qi * RR::CPL + qj] = (i < dy && j < dy) ? g[i * dy + j] : T(0);
+    }
+  }
+}
+
+// Measurement update with the masked observation staged in s; returns the log-likelihood
+// increment (uniform over the CTA).  filtering.py:84-130, with  Z = L^{-1} H P  so that
+// G S G^T = Z^T Z  and  G (y - yhat) = Z^T L^{-1} (y - yhat).  With H = I, R_t comes from registers.
 template <typename T, int D, bool HID>
-__device__ __forceinline__ T kalman_update(StepBuf<T, D>& s, int dx, int dy, int n_obs) {
-  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+__device__ __forceinline__ T kalman_update(StepBuf<T, D>& s, int dx, int dy, int n_obs,
+                                           const T (&Rr)[RowRegs<D>::N], bool rdiag) {
+  constexpr int LD = Tile<D>::LD;
+  using RR = RowRegs<D>;
   const int i = threadIdx.x;
   if (HID) {
     cta_sync<D>();
     if (i < dy) s.v[i] = s.mask[i] ? T(0) : s.y[i] - s.m[i] - s.c[i];
-    for (int e = i; e < dy * dx; e += NT) {
-      const int r = e / dx, q = e % dx;
-      const T p = s.P[r * LD + q];
-      s.U[r * LD + q] = s.mask[r] ? T(0) : p;
-      s.S[r * LD + q] = (s.mask[r] || s.mask[q]) ? s.R[r * LD + q] : p + s.R[r * LD + q];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool any_mask = n_obs < dy;
+#pragma unroll
+    for (int qi = 0; qi < RR::RPW; ++qi) {
+      const int r = w + qi * RR::NW;
+#pragma unroll
+      for (int qj = 0; qj < RR::CPL; ++qj) {
+        const int q = lane + 32 * qj;
+        if (r < dy && q < dx) {
+          const T p = s.P[r * LD + q];
+          T u = p, sv = p + (rdiag ? ((r == q) ? s.rd[r] : T(0)) : Rr[qi * RR::CPL + qj]);
+          if (any_mask) {
+            if (s.mask[r]) u = T(0);
+            if (s.mask[r] || s.mask[q]) sv = (r == q) ? T(1) : T(0);
+          }
+          s.U[r * LD + q] = u;
+          s.S[r * LD + q] = sv;
+        }
+      }
     }
     cta_sync<D>();
   } else {
@@ -171,10 +219,9 @@ __device__ __forceinline__ T kalman_update(StepBuf<T, D>& s, int dx, int dy, int
     mm_tn<T, D, 1>(s.W, s.Ht, s.S, s.R, dx);          // S = H P H^T + R
   }
   chol_inplace<T, D>(s.S, s.dg, dy);
-  fwd_solve<T, D>(s.S, s.U, s.v, dy, dx, s.dg);             // U <- Z = L^{-1} U ; v <- L^{-1} (y - yhat)
+  fwd_solve<T, D>(s.S, s.U, s.v, dy, dx, s.dg);       // U <- Z = L^{-1} U ; v <- L^{-1} (y - yhat)
   mm_tn<T, D, 2>(s.U, s.U, s.P, s.P, dy);             // P -= Z^T Z
   mv_tn<T, D, 1>(s.U, s.v, s.m, s.m, dy, dx);         // m += Z^T v
-  symmetrize<T, D>(s.P, dx);
   T part = T(0);
   if (i < dy && !s.mask[i]) part = T(-0.5) * s.v[i] * s.v[i] - log(s.dg[i]);
   T ell = cta_sum<T, D>(part, s.red) - T(n_obs) * half_log_2pi<T>();
@@ -194,12 +241,14 @@ template <typename T, int D> __device__ __forceinline__ void store_state(const F
 template <typename T, int D> __device__ __forceinline__ StepBuf<T, D> carve_step(Carve<T, D>& cv, bool hid) {
   StepBuf<T, D> s;
   s.P = cv.mat(); s.W = cv.mat(); s.S = cv.mat();
-  s.Ft = cv.mat(); s.Q = cv.mat(); s.R = cv.mat();
+  s.Ft = cv.mat(); s.Q = cv.mat();
+  s.R = hid ? nullptr : cv.mat();  // with H = I, R_t lives in registers (load_R_regs)
   // with H = I the update never needs W (P F^T is dead after the predict), so U shares its storage
   s.U = hid ? s.W : cv.mat();
   s.Ht = hid ? nullptr : cv.mat();
   s.m = cv.vec(); s.bv = cv.vec(); s.y = cv.vec(); s.c = cv.vec(); s.v = cv.vec(); s.red = cv.vec();
   s.dg = cv.p; cv.p += CholWs<D>::WORDS;
+  s.rd = cv.vec();
   s.mask = reinterpret_cast<int*>(cv.p);
   cv.p += (D * sizeof(int) + sizeof(T) - 1) / sizeof(T);
   s.h_clean = s.r_clean = s.c_clean = false;
@@ -207,7 +256,7 @@ template <typename T, int D> __device__ __forceinline__ StepBuf<T, D> carve_step
 }
 
 template <int D> __host__ __device__ constexpr size_t step_smem_elems(bool hid) {
-  return (size_t)(hid ? 6 : 8) * D * Tile<D>::LD + 10 * D + D /* mask, generous */ + 16;
+  return (size_t)(hid ? 5 : 8) * D * Tile<D>::LD + 11 * D + D /* mask, generous */ + 16;
 }
 
 // Runs t = t_begin .. t_end-1 of the recursion starting from the state in s (valid for t_begin-1),
@@ -216,26 +265,37 @@ template <typename T, int D, bool HID>
 __device__ __forceinline__ T run_recursion(const FilterArgs<T>& a, int c, int b, int t_begin, int t_end,
                                            StepBuf<T, D>& s) {
   const int dx = a.d.dx, dy = a.d.dy;
+  const bool rdiag = (a.d.flags & AUXSSM_FLAG_R_DIAGONAL) != 0;
   T ell = T(0);
+  T Rr[RowRegs<D>::N];
+#pragma unroll
+  for (int q = 0; q < RowRegs<D>::N; ++q) Rr[q] = T(0);
   bool first_dyn = true, first_obs = true;
   int t = t_begin;
   if (t == 0) {
     cta_sync<D>();
     if (threadIdx.x < dx) s.m[threadIdx.x] = a.m0[unit_off(a.d.m0, c, b) + threadIdx.x];
     load_mat<T, D, false>(a.P0 + unit_off(a.d.P0, c, b), s.P, dx, dx);
+    if (HID && !rdiag) load_R_regs<T, D>(a, c, b, 0, Rr);
     const int n_obs = stage_obs<T, D>(a, c, b, 0, true, s, nullptr, false);
     first_obs = false;
-    if (n_obs > 0) ell += kalman_update<T, D, HID>(s, dx, dy, n_obs);
+    if (n_obs > 0) {
+      ell += kalman_update<T, D, HID>(s, dx, dy, n_obs, Rr, rdiag);
+      symmetrize<T, D>(s.P, dx);
+    }
     store_state<T, D>(a, c, b, 0, s);
     t = 1;
   }
   for (; t < t_end; ++t) {
+    // R_t is requested first so that its DRAM latency hides behind the two predict products
+    if (HID && !rdiag && (first_obs || a.d.Rs.time != 0)) load_R_regs<T, D>(a, c, b, t, Rr);
     stage_dyn<T, D>(a, c, b, t - 1, first_dyn, s.Ft, nullptr, s.Q, s.bv);
     first_dyn = false;
     const int n_obs = stage_obs<T, D>(a, c, b, t, first_obs, s, nullptr, false);
     first_obs = false;
     kalman_predict<T, D>(s, dx);
-    if (n_obs > 0) ell += kalman_update<T, D, HID>(s, dx, dy, n_obs);
+    if (n_obs > 0) ell += kalman_update<T, D, HID>(s, dx, dy, n_obs, Rr, rdiag);
+    symmetrize<T, D>(s.P, dx);
     store_state<T, D>(a, c, b, t, s);
   }
   return ell;
@@ -250,7 +310,7 @@ __device__ __forceinline__ void chunk_range(int j, int chunk_len, int T, int& t0
 
 // pass A (chunk 0) and pass C (chunks >= 1): the recursion over one chunk.
 template <typename T, int D, bool HID>
-__global__ void __launch_bounds__(Tile<D>::NT) filter_recursion_kernel(FilterArgs<T> a, int chunk_first) {
+__global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) filter_recursion_kernel(FilterArgs<T> a, int chunk_first) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Carve<T, D> cv{reinterpret_cast<T*>(smem_raw)};
   constexpr int NT = Tile<D>::NT;
@@ -292,7 +352,7 @@ template <typename T, int D> struct ScanBuf {
 };
 
 template <int D> __host__ __device__ constexpr size_t scan_smem_elems() {
-  return (size_t)13 * D * Tile<D>::LD + 6 * D + 10 * D + D + 2 * D /* perm, ired */ + 32;
+  return (size_t)13 * D * Tile<D>::LD + 6 * D + 11 * D + D + 2 * D /* perm, ired */ + 32;
 }
 
 // Element (A, b, C, eta, J) of time step t (t >= 1, not the first element of the scan), with A
@@ -383,6 +443,7 @@ __device__ __forceinline__ void carve_scan_tail(Carve<T, D>& cv, StepBuf<T, D>& 
   s.P = s.W = s.S = s.U = s.Ft = s.Q = s.Ht = s.R = nullptr;
   s.m = cv.vec(); s.bv = cv.vec(); s.y = cv.vec(); s.c = cv.vec(); s.v = cv.vec(); s.red = cv.vec();
   s.dg = cv.p; cv.p += CholWs<D>::WORDS;
+  s.rd = cv.vec();
   s.mask = reinterpret_cast<int*>(cv.p);
   cv.p += (D * sizeof(int) + sizeof(T) - 1) / sizeof(T);
   sc.perm = reinterpret_cast<int*>(cv.p);
@@ -394,7 +455,7 @@ __device__ __forceinline__ void carve_scan_tail(Carve<T, D>& cv, StepBuf<T, D>& 
 
 // pass A for chunks 1..n-2: aggregate = elem(t0) (x) elem(t0+1) (x) ... (x) elem(t1-1)
 template <typename T, int D>
-__global__ void __launch_bounds__(Tile<D>::NT) filter_aggregate_kernel(FilterArgs<T> a) {
+__global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) filter_aggregate_kernel(FilterArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Carve<T, D> cv{reinterpret_cast<T*>(smem_raw)};
   constexpr int NT = Tile<D>::NT;
@@ -436,7 +497,7 @@ __global__ void __launch_bounds__(Tile<D>::NT) filter_aggregate_kernel(FilterArg
 
 // pass B: prefix_j = prefix_{j-1} (x) aggregate_j for j = 1..n-2, (b, C) components only.
 template <typename T, int D>
-__global__ void __launch_bounds__(Tile<D>::NT) filter_prefix_kernel(FilterArgs<T> a) {
+__global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) filter_prefix_kernel(FilterArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Carve<T, D> cv{reinterpret_cast<T*>(smem_raw)};
   constexpr int NT = Tile<D>::NT;

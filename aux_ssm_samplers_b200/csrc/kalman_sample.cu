@@ -115,7 +115,7 @@ __device__ __forceinline__ void store_x(const SampleArgs<T>& a, int c, int b, in
 
 // pass A, last chunk (and the whole job when n_chunks == 1): direct recursion.
 template <typename T, int D>
-__global__ void __launch_bounds__(Tile<D>::NT) sample_recursion_kernel(SampleArgs<T> a) {
+__global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) sample_recursion_kernel(SampleArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SCarve<T, D> cv{reinterpret_cast<T*>(smem_raw)};
   constexpr int NT = Tile<D>::NT, LD = Tile<D>::LD;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(Tile<D>::NT) sample_recursion_kernel(SampleArg
 
 // pass A, chunks 0..n-2: explicit (G_t, e_t), stored; composite folded from the chunk's last step down.
 template <typename T, int D>
-__global__ void __launch_bounds__(Tile<D>::NT) sample_aggregate_kernel(SampleArgs<T> a) {
+__global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) sample_aggregate_kernel(SampleArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SCarve<T, D> cv{reinterpret_cast<T*>(smem_raw)};
   constexpr int NT = Tile<D>::NT, LD = Tile<D>::LD;

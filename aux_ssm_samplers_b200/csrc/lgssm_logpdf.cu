@@ -44,7 +44,7 @@ template <int D> __host__ __device__ constexpr size_t logpdf_smem_elems() {
 }
 
 template <typename T, int D>
-__global__ void __launch_bounds__(Tile<D>::NT) lgssm_logpdf_kernel(LogpdfArgs<T> a) {
+__global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) lgssm_logpdf_kernel(LogpdfArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* p = reinterpret_cast<T*>(smem_raw);
   constexpr int NT = Tile<D>::NT, LD = Tile<D>::LD;
@@ -121,7 +121,12 @@ __global__ void __launch_bounds__(Tile<D>::NT) lgssm_logpdf_kernel(LogpdfArgs<T>
       }
       if (first_obs || a.d.Rs.time != 0) {
         cta_sync<D>();
-        load_mat<T, D, false>(a.Rs + unit_off(a.d.Rs, c, b) + (int64_t)t * a.d.Rs.time, LR, dy, dy);
+        const T* gr = a.Rs + unit_off(a.d.Rs, c, b) + (int64_t)t * a.d.Rs.time;
+        if (a.d.flags & AUXSSM_FLAG_R_DIAGONAL) {
+          AUXSSM_FOR_ROWS(ri, rj, dy, dy) LR[ri * LD + rj] = (ri == rj) ? gr[ri] : T(0);
+        } else {
+          load_mat<T, D, false>(gr, LR, dy, dy);
+        }
         chol_inplace<T, D>(LR, dgR, dy);
       }
       first_obs = false;
@@ -143,6 +148,158 @@ __global__ void __launch_bounds__(Tile<D>::NT) lgssm_logpdf_kernel(LogpdfArgs<T>
   if (threadIdx.x == 0) a.partial[(int64_t)unit * a.n_tiles + tile] = total;
 }
 
+// ---- fast path: time-invariant dynamics (and, for the likelihood part, H = I with diagonal R) -------
+// prep: one CTA per unit factors Q (and P0) once and evaluates the t = 0 terms; main: ONE THREAD PER
+// TIME STEP, residual and forward substitution in registers, F / chol(Q) read as shared broadcasts.
+
+template <typename T> struct LogpdfFastArgs {
+  LogpdfArgs<T> a;
+  T* prep;  // [units][dx*dx (chol Q) + dx (1/diag) + 2]   (+0: -sum log diag - dx/2 log 2pi, +1: t = 0 prior term)
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) logpdf_prep_kernel(LogpdfFastArgs<T> fa) {
+  const LogpdfArgs<T>& a = fa.a;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* p = reinterpret_cast<T*>(smem_raw);
+  constexpr int NT = Tile<D>::NT, LD = Tile<D>::LD;
+  for (int e = threadIdx.x; e < D * LD + 2 * D + CholWs<D>::WORDS; e += NT) p[e] = T(0);
+  __syncthreads();
+  T* L = p; p += D * LD;
+  T* r = p; p += D;
+  T* red = p; p += D;
+  T* dg = p; p += CholWs<D>::WORDS;
+  const int unit = blockIdx.x, c = unit / a.d.n_batch, b = unit % a.d.n_batch;
+  const int dx = a.d.dx, i = threadIdx.x;
+  T* out = fa.prep + (int64_t)unit * (dx * dx + dx + 2);
+  // t = 0 term: log N(x_0; m0, P0)
+  load_mat<T, D, false>(a.P0 + unit_off(a.d.P0, c, b), L, dx, dx);
+  if (i < dx) r[i] = a.xs[unit_off(a.d.xs, c, b) + i] - a.m0[unit_off(a.d.m0, c, b) + i];
+  chol_inplace<T, D>(L, dg, dx);
+  T term = gauss_logpdf<T, D>(L, r, red, dx, dg);
+  if (!(term == term)) term = T(0);
+  cta_sync<D>();
+  if (a.d.T > 1) {
+    load_mat<T, D, false>(a.Qs + unit_off(a.d.Qs, c, b), L, dx, dx);
+    chol_inplace<T, D>(L, dg, dx);
+    store_mat<T, D>(out, L, dx, dx);
+    T part = T(0);
+    if (i < dx) {
+      const T lii = L[i * LD + i];
+      out[dx * dx + i] = finite_(lii) ? T(1) / lii : T(0);
+      if (finite_(lii)) part = -log(fabs(lii)) - half_log_2pi_<T>();
+    }
+    const T cst = cta_sum<T, D>(part, red);
+    if (i == 0) out[dx * dx + dx] = cst;
+  }
+  if (i == 0) out[dx * dx + dx + 1] = term;
+}
+
+template <typename T, int D, int NTB>
+__global__ void __launch_bounds__(NTB) logpdf_fast_kernel(LogpdfFastArgs<T> fa) {
+  const LogpdfArgs<T>& a = fa.a;
+  constexpr int V = (D >= 4) ? 4 : D;
+  __shared__ __align__(16) T sF[D * D];
+  __shared__ __align__(16) T sL[D * D];
+  __shared__ T sb[D], sinv[D], sc[D];
+  __shared__ T sred[NTB / 32];
+  const int unit = blockIdx.x, c = unit / a.d.n_batch, b = unit % a.d.n_batch;
+  const int dx = a.d.dx, Tn = a.d.T;
+  const bool do_prior = (a.which & AUXSSM_LOGPDF_PRIOR) != 0, do_lik = (a.which & AUXSSM_LOGPDF_LOGLIK) != 0;
+  const T* prep = fa.prep + (int64_t)unit * (dx * dx + dx + 2);
+  for (int e = threadIdx.x; e < D * D; e += NTB) {
+    const int i = e / D, k = e % D;  // D is a compile-time power of two
+    const bool in = (i < dx && k < dx);
+    sF[e] = (do_prior && in && Tn > 1) ? a.Fs[unit_off(a.d.Fs, c, b) + i * dx + k] : T(0);
+    sL[e] = (do_prior && in && Tn > 1) ? prep[i * dx + k] : T(0);
+  }
+  if (threadIdx.x < D) {
+    const int i = threadIdx.x;
+    sb[i] = (do_prior && i < dx && Tn > 1) ? a.bs[unit_off(a.d.bs, c, b) + i] : T(0);
+    sinv[i] = (do_prior && i < dx && Tn > 1) ? prep[dx * dx + i] : T(0);
+    sc[i] = (do_lik && a.cs != nullptr && i < dx) ? a.cs[unit_off(a.d.cs, c, b) + i] : T(0);
+  }
+  __syncthreads();
+  const T cst = (do_prior && Tn > 1) ? prep[dx * dx + dx] : T(0);
+  const int t = blockIdx.y * NTB + threadIdx.x;
+  T total = T(0);
+  if (t < Tn) {
+    const T* xg = a.xs + unit_off(a.d.xs, c, b) + (int64_t)t * a.d.xs.time;
+    T x[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = (i < dx) ? xg[i] : T(0);
+    if (do_prior && t > 0) {
+      const T* xp = xg - a.d.xs.time;
+      T z[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) z[i] = (i < dx) ? xp[i] : T(0);  // z <- x_{t-1}
+      T r[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        T acc0 = sb[i], acc1 = T(0);
+#pragma unroll
+        for (int k = 0; k < D; k += V) {
+          T f[V];
+          ldv<T, V>(f, sF + i * D + k);
+#pragma unroll
+          for (int q = 0; q < V; ++q) {
+            if ((q & 1) == 0) acc0 = fma_(f[q], z[k + q], acc0); else acc1 = fma_(f[q], z[k + q], acc1);
+          }
+        }
+        r[i] = x[i] - (acc0 + acc1);
+      }
+      T quad = T(0);
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        T acc0 = r[i], acc1 = T(0);
+#pragma unroll
+        for (int k = 0; k < ((i + V - 1) / V) * V; k += V) {
+          T l[V];
+          ldv<T, V>(l, sL + i * D + k);
+#pragma unroll
+          for (int q = 0; q < V; ++q) {
+            if (k + q < i) {
+              if ((q & 1) == 0) acc0 = fma_(-l[q], z[k + q], acc0); else acc1 = fma_(-l[q], z[k + q], acc1);
+            }
+          }
+        }
+        z[i] = (acc0 + acc1) * sinv[i];  // z now holds chol(Q)^{-1} r (entries < i already overwritten)
+        quad = fma_(z[i], z[i], quad);
+      }
+      T term = T(-0.5) * quad + cst;
+      if (!(term == term)) term = T(0);
+      total += term;
+    }
+    if (do_lik) {  // H = I, diagonal R
+      const T* yg = a.ys + unit_off(a.d.ys, c, b) + (int64_t)t * a.d.ys.time;
+      const T* rg = a.Rs + unit_off(a.d.Rs, c, b) + (int64_t)t * a.d.Rs.time;
+      T term = T(0);
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        if (i < dx) {
+          const T rr = rg[i];
+          const T lii = sqrt(rr);  // chol of the diagonal matrix; NaN / inf entries follow mvn/base.py:49-57
+          const T e = (yg[i] - x[i] - sc[i]) / lii;
+          if (finite_(lii)) term += T(-0.5) * e * e - log(lii) - half_log_2pi_<T>();
+          else term += T(-0.5) * e * e;
+        }
+      }
+      if (!(term == term)) term = T(0);
+      total += term;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T sum = T(0);
+    for (int q = 0; q < NTB / 32; ++q) sum += sred[q];
+    if (blockIdx.y == 0 && do_prior) sum += prep[dx * dx + dx + 1];
+    a.partial[(int64_t)unit * a.n_tiles + blockIdx.y] = sum;
+  }
+}
+
 template <typename T>
 __global__ void logpdf_reduce_kernel(const T* partial, const T* ell, T* out, int n_chains, int per_chain,
                                      int minus_ell) {
@@ -156,12 +313,36 @@ __global__ void logpdf_reduce_kernel(const T* partial, const T* ell, T* out, int
 
 struct LogpdfPlan {
   int n_tiles, tile_len;
-  size_t total;
+  bool fast;
+  size_t off_prep, total;
 };
 
-static LogpdfPlan make_logpdf_plan(const auxssm_lgssm_desc* d, size_t es) {
+constexpr int kFastThreads = 128;
+
+static bool logpdf_fast_ok(const auxssm_lgssm_desc* d, uint32_t which) {
+  const int dmax = d->dx > d->dy ? d->dx : d->dy;
+  if (dmax > 32) return false;
+  if ((which & AUXSSM_LOGPDF_PRIOR) && d->T > 1 && (d->Fs.time != 0 || d->Qs.time != 0 || d->bs.time != 0))
+    return false;
+  if (which & AUXSSM_LOGPDF_LOGLIK) {
+    if (!(d->flags & AUXSSM_FLAG_H_IDENTITY) || !(d->flags & AUXSSM_FLAG_R_DIAGONAL)) return false;
+    if (d->cs.time != 0) return false;
+  }
+  return true;
+}
+
+static LogpdfPlan make_logpdf_plan(const auxssm_lgssm_desc* d, size_t es, uint32_t which) {
   LogpdfPlan p;
   const long units = (long)d->n_chains * d->n_batch;
+  p.fast = logpdf_fast_ok(d, which);
+  if (p.fast) {
+    p.tile_len = kFastThreads;
+    p.n_tiles = (d->T + kFastThreads - 1) / kFastThreads;
+    p.off_prep = ((size_t)units * p.n_tiles * es + 255) / 256 * 256;
+    p.total = p.off_prep + ((size_t)units * ((size_t)d->dx * d->dx + d->dx + 2) * es + 255) / 256 * 256;
+    return p;
+  }
+  p.off_prep = 0;
   long want = (8L * device_sm_count() + units - 1) / units;
   long cap = d->T / 8;
   if (cap < 1) cap = 1;
@@ -171,6 +352,21 @@ static LogpdfPlan make_logpdf_plan(const auxssm_lgssm_desc* d, size_t es) {
   p.n_tiles = (d->T + p.tile_len - 1) / p.tile_len;
   p.total = ((size_t)units * p.n_tiles * es + 255) / 256 * 256;
   return p;
+}
+
+template <typename T, int D> static int launch_logpdf_fast(cudaStream_t st, const LogpdfArgs<T>& a, T* prep) {
+  const int units = a.d.n_chains * a.d.n_batch;
+  LogpdfFastArgs<T> fa;
+  fa.a = a;
+  fa.prep = prep;
+  if (a.which & AUXSSM_LOGPDF_PRIOR) {
+    const size_t smem = ((size_t)D * Tile<D>::LD + 2 * D + CholWs<D>::WORDS) * sizeof(T);
+    logpdf_prep_kernel<T, D><<<units, Tile<D>::NT, smem, st>>>(fa);
+    AUXSSM_CHECK_LAUNCH("auxssm_lgssm_logpdf (prep)");
+  }
+  logpdf_fast_kernel<T, D, kFastThreads><<<dim3(units, a.n_tiles), kFastThreads, 0, st>>>(fa);
+  AUXSSM_CHECK_LAUNCH("auxssm_lgssm_logpdf (fast)");
+  return AUXSSM_OK;
 }
 
 template <typename T, int D> static int launch_logpdf(cudaStream_t st, const LogpdfArgs<T>& a) {
@@ -197,7 +393,7 @@ static int logpdf_entry(void* stream, const auxssm_lgssm_desc* d, uint32_t which
     set_error("%s: null data pointer", who);
     return AUXSSM_ERR_INVALID;
   }
-  const LogpdfPlan p = make_logpdf_plan(d, sizeof(T));
+  const LogpdfPlan p = make_logpdf_plan(d, sizeof(T), which);
   if (scratch_bytes < p.total || scratch == nullptr) {
     set_error("%s: scratch too small (%zu < %zu bytes)", who, scratch_bytes, p.total);
     return AUXSSM_ERR_SCRATCH;
@@ -212,7 +408,12 @@ static int logpdf_entry(void* stream, const auxssm_lgssm_desc* d, uint32_t which
   a.tile_len = p.tile_len;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int dmax = d->dx > d->dy ? d->dx : d->dy;
-  switch (padded_dim(dmax)) {
+  T* prep = reinterpret_cast<T*>(static_cast<unsigned char*>(scratch) + p.off_prep);
+  switch (padded_dim(dmax) * (p.fast ? -1 : 1)) {
+    case -4: rc = launch_logpdf_fast<T, 4>(st, a, prep); break;
+    case -8: rc = launch_logpdf_fast<T, 8>(st, a, prep); break;
+    case -16: rc = launch_logpdf_fast<T, 16>(st, a, prep); break;
+    case -32: rc = launch_logpdf_fast<T, 32>(st, a, prep); break;
     case 4: rc = launch_logpdf<T, 4>(st, a); break;
     case 8: rc = launch_logpdf<T, 8>(st, a); break;
     case 16: rc = launch_logpdf<T, 16>(st, a); break;
@@ -231,7 +432,10 @@ static int logpdf_entry(void* stream, const auxssm_lgssm_desc* d, uint32_t which
 
 extern "C" __attribute__((visibility("default"))) size_t auxssm_lgssm_logpdf_scratch_bytes(const auxssm_lgssm_desc* desc, int32_t elem_size) {
   if (auxssm::check_desc(desc, "auxssm_lgssm_logpdf_scratch_bytes")) return 0;
-  return auxssm::make_logpdf_plan(desc, (size_t)elem_size).total;
+  const size_t a = auxssm::make_logpdf_plan(desc, (size_t)elem_size, AUXSSM_LOGPDF_POSTERIOR).total;
+  const size_t b = auxssm::make_logpdf_plan(desc, (size_t)elem_size, AUXSSM_LOGPDF_PRIOR).total;
+  const size_t c = auxssm::make_logpdf_plan(desc, (size_t)elem_size, AUXSSM_LOGPDF_LOGLIK).total;
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 extern "C" __attribute__((visibility("default"))) int32_t auxssm_lgssm_logpdf_f32(void* stream, const auxssm_lgssm_desc* desc, uint32_t which,
                                            const float* ys, const float* xs, const float* ell, const float* m0,

@@ -24,6 +24,12 @@ template <> struct Tile<16> { static constexpr int LD = 20, NT = 32,  TM = 2, TN
 template <> struct Tile<32> { static constexpr int LD = 36, NT = 64,  TM = 4, TN = 4; };
 template <> struct Tile<64> { static constexpr int LD = 68, NT = 256, TM = 4, TN = 4; };
 
+// Resident CTAs per SM the kernels are compiled for: caps registers at 128/thread for D <= 32 so that
+// 7-8 chains per SM stay co-resident (1024 chains = one wave on 148 SMs).
+template <typename T, int D> struct Occ {
+  static constexpr int MINB = (D <= 32) ? (sizeof(T) == 4 ? 512 : 256) / Tile<D>::NT : 1;
+};
+
 template <int D> __device__ __forceinline__ void cta_sync() {
   if (Tile<D>::NT == 32) __syncwarp(); else __syncthreads();
 }
@@ -135,27 +141,43 @@ template <typename T, int D> __device__ __forceinline__ void zero_mat(T* A) {
   for (int i = threadIdx.x; i < D * LD; i += NT) A[i] = T(0);
 }
 
+// ---- element-wise helpers: warp w owns rows w, w + NW, ...; lanes run over columns.  No integer
+// division, global accesses are row-contiguous (coalesced), shared accesses are conflict-free.
+#define AUXSSM_FOR_ROWS(r, c, rows, cols)                                             \
+  for (int r = (int)(threadIdx.x >> 5); r < (rows); r += Tile<D>::NT / 32)           \
+    for (int c = (int)(threadIdx.x & 31); c < (cols); c += 32)
+
 // dst = src^T: dst[j][i] = src[i][j] for i < rows, j < cols, zero elsewhere (whole D x D tile).
 template <typename T, int D> __device__ __forceinline__ void transpose_to(const T* src, T* dst, int rows, int cols) {
-  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  constexpr int LD = Tile<D>::LD;
   cta_sync<D>();
-  for (int e = threadIdx.x; e < D * D; e += NT) {
-    const int i = e / D, j = e % D;  // dst[i][j] = src[j][i]
-    dst[i * LD + j] = (j < rows && i < cols) ? src[j * LD + i] : T(0);
-  }
+  AUXSSM_FOR_ROWS(i, j, D, D) dst[i * LD + j] = (j < rows && i < cols) ? src[j * LD + i] : T(0);
   cta_sync<D>();
 }
 
-// A = 0.5 (A + A^T) on the n x n block.
+// A = 0.5 (A + A^T) on the n x n block (reads into registers, barrier, writes).
 template <typename T, int D> __device__ __forceinline__ void symmetrize(T* A, int n) {
-  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  constexpr int LD = Tile<D>::LD, NW = Tile<D>::NT / 32, RPW = (D + NW - 1) / NW, CPL = (D + 31) / 32;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   cta_sync<D>();
-  for (int e = threadIdx.x; e < n * n; e += NT) {
-    const int i = e / n, j = e % n;
-    if (i < j) {
-      const T v = T(0.5) * (A[i * LD + j] + A[j * LD + i]);
-      A[i * LD + j] = v;
-      A[j * LD + i] = v;
+  T v[RPW * CPL];
+#pragma unroll
+  for (int qi = 0; qi < RPW; ++qi) {
+    const int i = w + qi * NW;
+#pragma unroll
+    for (int qj = 0; qj < CPL; ++qj) {
+      const int j = lane + 32 * qj;
+      v[qi * CPL + qj] = (i < n && j < n) ? T(0.5) * (A[i * LD + j] + A[j * LD + i]) : T(0);
+    }
+  }
+  cta_sync<D>();
+#pragma unroll
+  for (int qi = 0; qi < RPW; ++qi) {
+    const int i = w + qi * NW;
+#pragma unroll
+    for (int qj = 0; qj < CPL; ++qj) {
+      const int j = lane + 32 * qj;
+      if (i < n && j < n) A[i * LD + j] = v[qi * CPL + qj];
     }
   }
   cta_sync<D>();
@@ -163,41 +185,50 @@ template <typename T, int D> __device__ __forceinline__ void symmetrize(T* A, in
 
 // Copy the logical block [rows x cols] between shared buffers.
 template <typename T, int D> __device__ __forceinline__ void copy_mat(const T* src, T* dst, int rows, int cols) {
-  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  constexpr int LD = Tile<D>::LD;
   cta_sync<D>();
-  for (int e = threadIdx.x; e < rows * cols; e += NT) {
-    const int i = e / cols, j = e % cols;
-    dst[i * LD + j] = src[i * LD + j];
-  }
+  AUXSSM_FOR_ROWS(i, j, rows, cols) dst[i * LD + j] = src[i * LD + j];
   cta_sync<D>();
 }
 
 // Load a [rows x cols] row-major contiguous global block into shared (optionally transposed).
+// All global loads are issued before the first shared store (memory-level parallelism).
 template <typename T, int D, bool TRANS>
 __device__ __forceinline__ void load_mat(const T* __restrict__ g, T* s, int rows, int cols) {
-  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
-  for (int e = threadIdx.x; e < rows * cols; e += NT) {
-    const int i = e / cols, j = e % cols;
-    const T v = g[e];
-    if (TRANS) s[j * LD + i] = v; else s[i * LD + j] = v;
+  constexpr int LD = Tile<D>::LD, NW = Tile<D>::NT / 32, RPW = (D + NW - 1) / NW, CPL = (D + 31) / 32;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  T v[RPW * CPL];
+#pragma unroll
+  for (int qi = 0; qi < RPW; ++qi) {
+    const int i = w + qi * NW;
+#pragma unroll
+    for (int qj = 0; qj < CPL; ++qj) {
+      const int j = lane + 32 * qj;
+      v[qi * CPL + qj] = (i < rows && j < cols) ? g[i * cols + j] : T(0);
+    }
+  }
+#pragma unroll
+  for (int qi = 0; qi < RPW; ++qi) {
+    const int i = w + qi * NW;
+#pragma unroll
+    for (int qj = 0; qj < CPL; ++qj) {
+      const int j = lane + 32 * qj;
+      if (i < rows && j < cols) {
+        if (TRANS) s[j * LD + i] = v[qi * CPL + qj]; else s[i * LD + j] = v[qi * CPL + qj];
+      }
+    }
   }
 }
 template <typename T, int D>
 __device__ __forceinline__ void store_mat(T* __restrict__ g, const T* s, int rows, int cols) {
-  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
-  for (int e = threadIdx.x; e < rows * cols; e += NT) {
-    const int i = e / cols, j = e % cols;
-    g[e] = s[i * LD + j];
-  }
+  constexpr int LD = Tile<D>::LD;
+  AUXSSM_FOR_ROWS(i, j, rows, cols) g[i * cols + j] = s[i * LD + j];
 }
 template <typename T, int D>
 __device__ __forceinline__ void store_mat_t(T* __restrict__ g, const T* s, int rows, int cols) {
   // global [rows x cols] <- transpose of shared [cols x rows]
-  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
-  for (int e = threadIdx.x; e < rows * cols; e += NT) {
-    const int i = e / cols, j = e % cols;
-    g[e] = s[j * LD + i];
-  }
+  constexpr int LD = Tile<D>::LD;
+  AUXSSM_FOR_ROWS(i, j, rows, cols) g[i * cols + j] = s[j * LD + i];
 }
 
 // 1 / sqrt(x) and sqrt(x) for a Cholesky pivot.  fp32: MUFU.RSQ + one Newton step (full fp32 accuracy,

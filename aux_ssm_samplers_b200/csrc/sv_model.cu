@@ -31,7 +31,7 @@ template <typename T>
 __global__ void sv_obs_factory_kernel(int order, int64_t n_chains, int64_t Tn, int d, const T* __restrict__ ys,
                                       int64_t ys_chain_stride, const T* __restrict__ x, const T* __restrict__ u,
                                       const T* __restrict__ delta, int delta_stride, T* __restrict__ aux_ys,
-                                      T* __restrict__ Rs) {
+                                      T* __restrict__ Rdiag) {
   const int64_t total = n_chains * Tn * d;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t c = e / (Tn * d);
@@ -47,6 +47,7 @@ __global__ void sv_obs_factory_kernel(int order, int64_t n_chains, int64_t Tn, i
     } else {
       const T omega = T(1) / (-hess + T(2) / dl);
       aux_ys[e] = omega * (T(2) * uv / dl + grad - hess * xv);
+      if (Rdiag) Rdiag[e] = omega;  // diagonal layout: R[c, t, i]
     }
   }
 }
@@ -72,15 +73,15 @@ __global__ void sv_second_order_R_kernel(int64_t n_chains, int64_t Tn, int d, co
   }
 }
 
-// R[c] = (delta_c / 2) I   (first order; one d x d block per chain, time stride 0)
+// R[c] = (delta_c / 2) I   (first order; one block per chain, time stride 0); dense d x d or diagonal d
 template <typename T>
 __global__ void sv_first_order_R_kernel(int64_t n_chains, int d, const T* __restrict__ delta, int delta_stride,
-                                        T* __restrict__ Rs) {
-  const int64_t total = n_chains * d * d;
+                                        T* __restrict__ Rs, int dense) {
+  const int64_t per = dense ? (int64_t)d * d : d, total = n_chains * per;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = e / (d * d);
-    const int r = (int)(e % (d * d));
-    Rs[e] = (r / d == r % d) ? T(0.5) * delta[c * delta_stride] : T(0);
+    const int64_t c = e / per;
+    const int r = (int)(e % per);
+    Rs[e] = (!dense || r / d == r % d) ? T(0.5) * delta[c * delta_stride] : T(0);
   }
 }
 
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(NT) sv_log_potential_kernel(int64_t n_per_chai
 template <typename T>
 static int sv_factory_entry(void* stream, int32_t order, int64_t n_chains, int64_t Tn, int32_t d, const T* ys,
                             int64_t ys_chain_stride, const T* x, const T* u, const T* delta, int32_t delta_stride,
-                            T* aux_ys, T* Rs) {
+                            T* aux_ys, T* Rs, int32_t dense_R) {
   if ((order != 1 && order != 2) || n_chains < 1 || Tn < 1 || d < 1 || !ys || !x || !u || !delta || !aux_ys || !Rs ||
       (delta_stride != 0 && delta_stride != 1)) {
     set_error("auxssm_sv_obs_factory: invalid argument");
@@ -122,13 +123,15 @@ static int sv_factory_entry(void* stream, int32_t order, int64_t n_chains, int64
   const int64_t cap = 32L * device_sm_count();
   if (blocks > cap) blocks = cap;
   sv_obs_factory_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(order, n_chains, Tn, d, ys, ys_chain_stride, x, u, delta,
-                                                              delta_stride, aux_ys, Rs);
+                                                              delta_stride, aux_ys,
+                                                              (order == 2 && !dense_R) ? Rs : nullptr);
   AUXSSM_CHECK_LAUNCH("auxssm_sv_obs_factory");
   if (order == 1) {
-    const int64_t tot = n_chains * d * d;
-    sv_first_order_R_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n_chains, d, delta, delta_stride, Rs);
+    const int64_t tot = n_chains * (dense_R ? (int64_t)d * d : d);
+    sv_first_order_R_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n_chains, d, delta, delta_stride, Rs,
+                                                                            dense_R);
     AUXSSM_CHECK_LAUNCH("auxssm_sv_obs_factory (R)");
-  } else {
+  } else if (dense_R) {
     int64_t rb = (total * d + 255) / 256;
     if (rb > 64 * cap) rb = 64 * cap;
     sv_second_order_R_kernel<T><<<(unsigned)rb, 256, 0, st>>>(n_chains, Tn, d, ys, ys_chain_stride, x, delta,
@@ -155,16 +158,17 @@ static int sv_potential_entry(void* stream, int64_t n_chains, int64_t n_per_chai
 
 extern "C" __attribute__((visibility("default"))) int32_t auxssm_sv_obs_factory_f32(void* stream, int32_t order, int64_t n_chains, int64_t T, int32_t d,
                                              const float* ys, int64_t ys_chain_stride, const float* x, const float* u,
-                                             const float* delta, int32_t delta_stride, float* aux_ys, float* Rs) {
+                                             const float* delta, int32_t delta_stride, float* aux_ys, float* Rs,
+                                             int32_t dense_R) {
   return auxssm::sv_factory_entry<float>(stream, order, n_chains, T, d, ys, ys_chain_stride, x, u, delta, delta_stride,
-                                         aux_ys, Rs);
+                                         aux_ys, Rs, dense_R);
 }
 extern "C" __attribute__((visibility("default"))) int32_t auxssm_sv_obs_factory_f64(void* stream, int32_t order, int64_t n_chains, int64_t T, int32_t d,
                                              const double* ys, int64_t ys_chain_stride, const double* x,
                                              const double* u, const double* delta, int32_t delta_stride,
-                                             double* aux_ys, double* Rs) {
+                                             double* aux_ys, double* Rs, int32_t dense_R) {
   return auxssm::sv_factory_entry<double>(stream, order, n_chains, T, d, ys, ys_chain_stride, x, u, delta,
-                                          delta_stride, aux_ys, Rs);
+                                          delta_stride, aux_ys, Rs, dense_R);
 }
 extern "C" __attribute__((visibility("default"))) int32_t auxssm_sv_log_potential_f32(void* stream, int64_t n_chains, int64_t n_per_chain, const float* ys,
                                                int64_t ys_chain_stride, const float* x, float* out,

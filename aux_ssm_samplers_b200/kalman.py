@@ -40,6 +40,12 @@ class LGSSM(NamedTuple):
     cs: Optional[torch.Tensor]
 
 
+class Diagonal(NamedTuple):
+    """Wraps ``diag(R_t)`` of shape ``[..., T, dy]`` to be used as ``LGSSM.Rs`` when every observation
+    covariance is diagonal (B200-first layout: ``d`` instead of ``d^2`` values per step travel through HBM)."""
+    diag: torch.Tensor
+
+
 class KalmanSampler(NamedTuple):
     """Mirror of ``KalmanSampler(SamplerState)`` (kalman/generic.py:13-16)."""
     x: torch.Tensor
@@ -118,14 +124,18 @@ def _infer_dims(ys, m0, inner_batch, xs=None):
     return _Dims(C, B, T, dx, dy, has_chain, inner_batch)
 
 
-def _fill_desc(dims, parallel, time_chunks, hid):
+def _fill_desc(dims, parallel, time_chunks, hid, rdiag=False):
     d = LgssmDesc()
     d.T, d.dx, d.dy = dims.T, dims.dx, dims.dy
     d.n_chains, d.n_batch = dims.C, dims.B
     d.parallel = 1 if parallel else 0
     d.time_chunks = int(time_chunks)
-    d.flags = _lib.FLAG_H_IDENTITY if hid else 0
+    d.flags = (_lib.FLAG_H_IDENTITY if hid else 0) | (_lib.FLAG_R_DIAGONAL if rdiag else 0)
     return d
+
+
+def _tensors(lgssm):
+    return [t.diag if isinstance(t, Diagonal) else t for t in lgssm if t is not None]
 
 
 def _out_shape(dims, n_time, core):
@@ -157,7 +167,10 @@ def _prep_lgssm(d, dims, lgssm, dtype):
     else:
         out["Fs"] = out["Qs"] = out["bs"] = None
     out["Hs"], d.Hs = _canon(Hs, (dy, dx), dims.T, dims, "Hs")
-    out["Rs"], d.Rs = _canon(Rs, (dy, dy), dims.T, dims, "Rs")
+    if isinstance(Rs, Diagonal):
+        out["Rs"], d.Rs = _canon(Rs.diag, (dy,), dims.T, dims, "Rs (diagonal)")
+    else:
+        out["Rs"], d.Rs = _canon(Rs, (dy, dy), dims.T, dims, "Rs")
     out["cs"], d.cs = _canon(cs, (dy,), dims.T, dims, "cs")
     for k, v in out.items():
         if v is not None and v.dtype != dtype:
@@ -176,12 +189,12 @@ def filtering(ys, lgssm, parallel, *, inner_batch=False, time_chunks=0):
     ``time_chunks`` (parallel only) forces the number of time chunks of the scan; 0 = automatic.
     """
     lgssm = LGSSM(*lgssm)
-    dev = _lib.require_cuda(ys, *[t for t in lgssm if t is not None])
+    dev = _lib.require_cuda(ys, *_tensors(lgssm))
     dtype = ys.dtype
     sfx = _lib.suffix(dtype)
     dims = _infer_dims(ys, lgssm.m0, inner_batch)
     hid = lgssm.Hs is None
-    d = _fill_desc(dims, parallel, time_chunks, hid)
+    d = _fill_desc(dims, parallel, time_chunks, hid, isinstance(lgssm.Rs, Diagonal))
     p = _prep_lgssm(d, dims, lgssm, dtype)
     ysc, d.ys = _canon(ys, (dims.dy,), dims.T, dims, "ys")
     ms = torch.empty(_out_shape(dims, dims.T, (dims.dx,)), dtype=dtype, device=dev)
@@ -239,7 +252,7 @@ def _logpdf(which, ys, xs, ell, lgssm, inner_batch):
     dims = _infer_dims(ys, lgssm.m0, inner_batch, xs=xs)
     dims = dims._replace(dx=xs.shape[-1])
     hid = lgssm.Hs is None
-    d = _fill_desc(dims, False, 0, hid)
+    d = _fill_desc(dims, False, 0, hid, isinstance(lgssm.Rs, Diagonal))
     p = _prep_lgssm(d, dims, lgssm, dtype)
     ysc = None
     if ys is not None:

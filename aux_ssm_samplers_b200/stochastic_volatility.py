@@ -28,23 +28,25 @@ def get_dynamics(nu, phi, tau, rho, dim, dtype=torch.float64, device="cpu"):
     return mu, Q.clone(), F, Q, b
 
 
-def observations_factory(ys, x, u, delta, order):
-    """auxiliary_kalman.py:28-48.  ``x, u``: [C, T, d]; returns (aux_ys, Hs=None (identity), Rs, cs=None)."""
+def observations_factory(ys, x, u, delta, order, dense_R=False):
+    """auxiliary_kalman.py:28-48.  ``x, u``: [C, T, d]; returns (aux_ys, Hs=None (identity), Rs, cs=None).
+
+    Both factories produce DIAGONAL observation covariances ((delta/2) I, resp. Omega_t with a diagonal
+    Hessian, model.py:66-69).  By default they are returned as ``kalman.Diagonal([C, T or 1, d])``;
+    ``dense_R=True`` materialises ``[C, T or 1, d, d]`` exactly like the reference does."""
     dev = _lib.require_cuda(ys, x, u)
     sfx = _lib.suffix(x.dtype)
     C, T, d = x.shape
     x, u, ys = x.contiguous(), u.contiguous(), ys.contiguous()
     dl = kalman._as_delta(delta, C, x.dtype, dev)
     aux_ys = torch.empty_like(x)
-    if order == 1:
-        Rs = torch.empty((C, 1, d, d), dtype=x.dtype, device=dev)
-    else:
-        Rs = torch.empty((C, T, d, d), dtype=x.dtype, device=dev)
+    Tr = 1 if order == 1 else T
+    Rs = torch.empty((C, Tr, d, d) if dense_R else (C, Tr, d), dtype=x.dtype, device=dev)
     ys_stride = 0 if ys.dim() == 2 else T * d
     _lib.call("auxssm_sv_obs_factory_" + sfx,
         _lib.stream_ptr(dev), order, C, T, d, _lib.ptr(ys), ys_stride, _lib.ptr(x), _lib.ptr(u), _lib.ptr(dl),
-        1 if dl.numel() > 1 else 0, _lib.ptr(aux_ys), _lib.ptr(Rs))
-    return aux_ys, None, Rs, None
+        1 if dl.numel() > 1 else 0, _lib.ptr(aux_ys), _lib.ptr(Rs), 1 if dense_R else 0)
+    return aux_ys, None, (Rs if dense_R else kalman.Diagonal(Rs)), None
 
 
 def log_potential(ys, x, out=None):
@@ -63,7 +65,7 @@ def log_potential(ys, x, out=None):
     return out
 
 
-def get_kernel(ys, m0, P0, F, Q, b, parallel, order=1, *, time_chunks=0):
+def get_kernel(ys, m0, P0, F, Q, b, parallel, order=1, *, time_chunks=0, dense_R=False):
     """auxiliary_kalman.py:10-57: auxiliary Kalman sampler for the SV model, first or second order."""
     d = m0.shape[0]
     Fs, Qs, bs = F.reshape(1, d, d), Q.reshape(1, d, d), b.reshape(1, d)  # time-invariant: stride 0, never tiled
@@ -72,7 +74,7 @@ def get_kernel(ys, m0, P0, F, Q, b, parallel, order=1, *, time_chunks=0):
         return m0, P0, Fs, Qs, bs
 
     def obs_factory(x, u, delta):
-        return observations_factory(ys, x, u, delta, order)
+        return observations_factory(ys, x, u, delta, order, dense_R)
 
     prior_lgssm = kalman.LGSSM(m0, P0, Fs, Qs, bs, None, None, None)
 

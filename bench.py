@@ -172,7 +172,8 @@ def run_gpu(args):
     es = 4
     (m0, P0, F, Q, b), xs_true, ys = make_data(d, T, 20250002)
     to = lambda a: torch.as_tensor(np.asarray(a), dtype=dtype, device=device)
-    _, kernel = sv.get_kernel(to(ys), to(m0), to(P0), to(F), to(Q), to(b), parallel=True, order=order)
+    _, kernel = sv.get_kernel(to(ys), to(m0), to(P0), to(F), to(Q), to(b), parallel=True, order=order,
+                              dense_R=args.dense_r)
     rng = np.random.default_rng(20250002 + 17 * rank)
     x0 = (xs_true[None] + 0.3 * rng.standard_normal((C, T, d))).astype(np.float32)
 
@@ -254,7 +255,8 @@ def run_gpu(args):
     filt_calls, filt_ms = summ.get(filt_name, (0, 0.0))
     per_launch_ms = filt_ms / max(filt_calls, 1)
     units_launch = T * C
-    alg_bytes_unit = (2 * d * d + 2 * d) * es          # R_t, y_t in; P_t, m_t out (F, Q, b, H are stride-0)
+    r_elems = d * d if args.dense_r else d
+    alg_bytes_unit = (r_elems + d * d + 2 * d) * es    # R_t, y_t in; P_t, m_t out (F, Q, b, H are stride-0)
     survey_bytes_unit = (5 * d * d + 4 * d) * es       # SURVEY 8(d) operator-boundary figure for one filter
     flops_unit = (4 + 0 + 1.0 / 3 + 1 + 2) * d ** 3 * 2 / 2  # see DESIGN.md: ~7.3 d^3 flop with H = I
     peaks = {}
@@ -304,6 +306,7 @@ def run_gpu(args):
             "config": {"workload": "configs[1]: SV d=30 T=1024, 1024 chains/GPU, second-order aux-Kalman sweep",
                        "d": d, "T": T, "chains_per_gpu": C, "chains_total": C * world, "order": order,
                        "delta": delta, "parallel": True,
+                       "R_layout": "dense [C,T,d,d]" if args.dense_r else "diagonal [C,T,d] (Omega_t is diagonal)",
                        "time_chunks": "auto (=1: 1024 chains fill the SMs; see DESIGN.md)",
                        "l2": "inputs (>=3.7 GB of R_t per filter) exceed the 126 MB L2; no flush needed",
                        "draws": "externally supplied normals/uniforms (parity mode), 2 rotating sets"},
@@ -329,6 +332,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU (debug)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dense-r", action="store_true",
+                    help="materialise R_t = Omega_t as dense [C,T,d,d] like the reference (default: diagonal)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -53,6 +53,7 @@ typedef struct auxssm_stride {
 
 /* flags */
 #define AUXSSM_FLAG_H_IDENTITY 1u /* Hs == NULL: H_t = I (requires dy == dx), c_t = 0 if cs == NULL */
+#define AUXSSM_FLAG_R_DIAGONAL 2u /* Rs holds diag(R_t): core shape [dy] instead of [dy, dy]          */
 
 /*
  * Linear-Gaussian state-space model, mirrors the LGSSM NamedTuple
@@ -148,13 +149,16 @@ int32_t auxssm_kalman_mh_f64(void* stream, int64_t n_chains, int64_t n_per_chain
  * x, u, aux_ys are [n_chains, T, d] contiguous; ys is the data [T, d] (ys_chain_stride 0) or one
  * data set per chain (ys_chain_stride T*d).  order 1: aux_ys = u + (delta/2) nan_to_num(grad),
  * Rs[n_chains, d, d] = (delta/2) I (use Rs.time = 0).  order 2: Omega = (-hess + 2I/delta)^{-1},
- * aux_ys = Omega (2u/delta + grad - hess x), Rs[n_chains, T, d, d] = Omega (dense).              */
+ * aux_ys = Omega (2u/delta + grad - hess x), Rs[n_chains, T, d, d] = Omega (dense).
+ * dense_R = 0 writes only the diagonals (Rs[n_chains, 1 or T, d], for AUXSSM_FLAG_R_DIAGONAL).   */
 int32_t auxssm_sv_obs_factory_f32(void* stream, int32_t order, int64_t n_chains, int64_t T, int32_t d,
                                   const float* ys, int64_t ys_chain_stride, const float* x, const float* u,
-                                  const float* delta, int32_t delta_stride, float* aux_ys, float* Rs);
+                                  const float* delta, int32_t delta_stride, float* aux_ys, float* Rs,
+                                  int32_t dense_R);
 int32_t auxssm_sv_obs_factory_f64(void* stream, int32_t order, int64_t n_chains, int64_t T, int32_t d,
                                   const double* ys, int64_t ys_chain_stride, const double* x, const double* u,
-                                  const double* delta, int32_t delta_stride, double* aux_ys, double* Rs);
+                                  const double* delta, int32_t delta_stride, double* aux_ys, double* Rs,
+                                  int32_t dense_R);
 /* out[c] (+)= sum_{t,i} nan_to_num(log N(ys[t,i]; 0, exp(x[c,t,i]/2)))   (model.py:56-76)          */
 int32_t auxssm_sv_log_potential_f32(void* stream, int64_t n_chains, int64_t n_per_chain, const float* ys,
                                     int64_t ys_chain_stride, const float* x, float* out, int32_t accumulate);

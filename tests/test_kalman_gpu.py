@@ -186,7 +186,8 @@ def test_logpdfs_vs_oracle(dtype, dx, dy, T, C):
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("order,seed", [(1, 43), (2, 44)])
 @pytest.mark.parametrize("parallel", [False, True])
-def test_sv_sweep_vs_oracle(dtype, order, seed, parallel):
+@pytest.mark.parametrize("dense_R", [False, True])
+def test_sv_sweep_vs_oracle(dtype, order, seed, parallel, dense_R):
     """Full auxiliary-Kalman MH sweep on the SV model with identical externally supplied draws."""
     from aux_ssm_samplers_b200 import stochastic_volatility as sv
     from aux_ssm_samplers_b200.draws import ExternalDraws
@@ -199,7 +200,7 @@ def test_sv_sweep_vs_oracle(dtype, order, seed, parallel):
     facs = osv.make_factories(ys, m0, P0, F, Q, b, order)
     ex, eacc, aux = ok.kalman_sweep(x, delta, n_aux, n_eps, un, *facs, parallel)
     _, kernel = sv.get_kernel(dev(ys, dtype), dev(m0, dtype), dev(P0, dtype), dev(F, dtype), dev(Q, dtype),
-                              dev(b, dtype), parallel, order, time_chunks=3 if parallel else 0)
+                              dev(b, dtype), parallel, order, time_chunks=3 if parallel else 0, dense_R=dense_R)
     from aux_ssm_samplers_b200.kalman import KalmanSampler
     state = kernel(ExternalDraws(normals=[n_aux, n_eps], uniforms=[un]), KalmanSampler(dev(x, dtype), True), delta)
     torch.cuda.synchronize()
@@ -209,3 +210,63 @@ def test_sv_sweep_vs_oracle(dtype, order, seed, parallel):
     npt.assert_array_equal(host(state.updated).astype(bool), eacc)
     r = TOL[dtype]["rtol"]
     npt.assert_allclose(host(state.x), ex, rtol=r, atol=r * np.abs(ex).max() * 10)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("d,T,C", [(3, 11, 2), (30, 40, 3), (64, 9, 2)])
+@pytest.mark.parametrize("dense_h", [False, True])
+@pytest.mark.parametrize("chunks", [1, 3])
+def test_filter_and_logpdf_diagonal_R(dtype, d, T, C, dense_h, chunks):
+    """AUXSSM_FLAG_R_DIAGONAL: diag(R_t) passed as [C, T, d] must equal the dense-R oracle."""
+    from aux_ssm_samplers_b200 import kalman
+    if d == 64 and dtype == torch.float64 and (dense_h or chunks > 1):
+        pytest.skip("d=64 fp64 with dense H / parallel exceeds shared memory (documented)")
+    rng = np.random.default_rng(d + T + chunks)
+    ys, lg = random_lgssm(rng, T, d, d, lead=(C,), stable=True)
+    lg = list(lg)
+    rdiag = rng.uniform(0.05, 1.0, size=(C, T, d))
+    lg[6] = rdiag[..., :, None] * np.eye(d)
+    if not dense_h:
+        lg[5] = np.broadcast_to(np.eye(d), (C, T, d, d)).copy()
+        lg[7] = np.zeros((C, T, d))
+    ys[0, 2, 1] = np.nan
+    ys[-1, 4, :] = np.nan
+    ems, ePs, eell = ok.filtering(ys, lg, False)
+    glg = [dev(a, dtype) for a in lg]
+    glg[6] = kalman.Diagonal(dev(rdiag, dtype))
+    if not dense_h:
+        glg[5] = glg[7] = None
+    ms, Ps, ell = kalman.filtering(dev(ys, dtype), glg, chunks > 1, time_chunks=chunks)
+    r = TOL[dtype]["rtol"]
+    npt.assert_allclose(host(ms), ems, rtol=r, atol=r * max(1.0, np.abs(ems).max()))
+    npt.assert_allclose(host(Ps), ePs, rtol=r, atol=r * np.abs(ePs).max())
+    npt.assert_allclose(host(ell), eell, rtol=r)
+    xs = rng.standard_normal((C, T, d))
+    got = kalman.posterior_logpdf(dev(ys, dtype), dev(xs, dtype), dev(eell, dtype), glg)
+    npt.assert_allclose(host(got), ok.posterior_logpdf(ys, xs, eell, lg), rtol=r)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("d,T,C", [(1, 5, 2), (4, 300, 3), (30, 130, 2)])
+def test_logpdf_fast_path_time_invariant(dtype, d, T, C):
+    """Time-invariant (stride-0) dynamics + H = I + diagonal R take the thread-per-time-step kernel."""
+    from aux_ssm_samplers_b200 import kalman
+    rng = np.random.default_rng(100 + d)
+    _, lg = random_lgssm(rng, T, d, d, stable=True)
+    m0, P0, F, Q, b = lg[0], lg[1], lg[2][:1], lg[3][:1], lg[4][:1]
+    rdiag = rng.uniform(0.05, 1.0, size=(C, T, d))
+    ys = rng.standard_normal((C, T, d))
+    ys[0, 1, 0] = np.nan
+    xs = rng.standard_normal((C, T, d))
+    ell = rng.standard_normal(C)
+    full = (m0, P0, np.broadcast_to(F, (T - 1, d, d)), np.broadcast_to(Q, (T - 1, d, d)),
+            np.broadcast_to(b, (T - 1, d)), np.broadcast_to(np.eye(d), (T, d, d)),
+            rdiag[..., :, None] * np.eye(d), np.zeros((T, d)))
+    glg = kalman.LGSSM(dev(m0, dtype), dev(P0, dtype), dev(F, dtype), dev(Q, dtype), dev(b, dtype), None,
+                       kalman.Diagonal(dev(rdiag, dtype)), None)
+    r = TOL[dtype]["rtol"]
+    npt.assert_allclose(host(kalman.prior_logpdf(dev(xs, dtype), glg)), ok.prior_logpdf(xs, full), rtol=r)
+    npt.assert_allclose(host(kalman.log_likelihood(dev(ys, dtype), dev(xs, dtype), glg)),
+                        ok.log_likelihood(ys, xs, full), rtol=r)
+    npt.assert_allclose(host(kalman.posterior_logpdf(dev(ys, dtype), dev(xs, dtype), dev(ell, dtype), glg)),
+                        ok.posterior_logpdf(ys, xs, ell, full), rtol=r)
