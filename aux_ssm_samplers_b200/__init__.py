@@ -2,8 +2,11 @@
 
 ``kalman``                 auxiliary Kalman sampler (filter / backward sampler / log-densities / MH sweep)
 ``stochastic_volatility``  SV model adapters used by the headline benchmark
+``csmc``                   conditional SMC particle Gibbs (fused sweep + unfused primitives)
+``diagnostics``            cross-chain split-R-hat / ESS over all-gathered chain statistics
 ``draws``                  key stand-ins (externally supplied or device-generated draws)
 """
-from . import draws, kalman, stochastic_volatility  # noqa: F401
+from . import csmc, diagnostics, draws, kalman, stochastic_volatility  # noqa: F401
 from ._lib import AuxssmError  # noqa: F401
 from .kalman import LGSSM, get_kernel  # noqa: F401
+from .csmc import get_generic_kernel, get_independent_kernel  # noqa: F401

@@ -36,6 +36,19 @@ class LgssmDesc(ctypes.Structure):
     ]
 
 
+class CsmcDesc(ctypes.Structure):
+    _fields_ = [
+        ("T", ctypes.c_int32), ("N", ctypes.c_int32), ("d", ctypes.c_int32), ("n_chains", ctypes.c_int32),
+        ("proposal", ctypes.c_int32), ("potential", ctypes.c_int32), ("resampling", ctypes.c_int32),
+        ("backward", ctypes.c_int32), ("gradient", ctypes.c_int32),
+        ("ys_chain_stride", ctypes.c_int64), ("gains_time_stride", ctypes.c_int64), ("sig", ctypes.c_double),
+    ]
+
+
+PROP_BOOTSTRAP, PROP_INDEPENDENT, PROP_GUIDED = 0, 1, 2
+POT_FLAT, POT_GAUSSIAN, POT_SV = 0, 1, 2
+RESAMPLE_MULTINOMIAL, RESAMPLE_KILLING = 0, 1
+
 _P = ctypes.c_void_p
 _I32, _I64, _U32, _SZ = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_size_t
 _DESC = ctypes.POINTER(LgssmDesc)
@@ -55,6 +68,13 @@ _SIGNATURES = {
     "auxssm_kalman_mh_{s}": (_I32, [_P, _I64, _I64, _P, _I32] + [_P] * 10),
     "auxssm_sv_obs_factory_{s}": (_I32, [_P, _I32, _I64, _I64, _I32, _P, _I64, _P, _P, _P, _I32, _P, _P, _I32]),
     "auxssm_sv_log_potential_{s}": (_I32, [_P, _I64, _I64, _P, _I64, _P, _P, _I32]),
+    "auxssm_csmc_scratch_bytes": (_SZ, [ctypes.POINTER(CsmcDesc), _I32]),
+    "auxssm_csmc_sweep_{s}": (_I32, [_P, ctypes.POINTER(CsmcDesc)] + [_P] * 21 + [_P, _SZ]),
+    "auxssm_guided_gains_{s}": (_I32, [_P, _I32, _I32, _P, _P, _P, _P, _P]),
+    "auxssm_normalize_{s}": (_I32, [_P, _I64, _I32, _P, _P]),
+    "auxssm_resample_multinomial_{s}": (_I32, [_P, _I64, _I32, _P, _P, _P]),
+    "auxssm_resample_killing_{s}": (_I32, [_P, _I64, _I32, _P, _P, _P, _P]),
+    "auxssm_categorical_{s}": (_I32, [_P, _I64, _I32, _P, _P, _P]),
 }
 
 

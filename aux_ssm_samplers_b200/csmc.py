@@ -1,0 +1,375 @@
+"""Conditional SMC particle Gibbs on B200: host-side mirror of the reference's cSMC API.
+
+Same names and argument meaning as the reference:
+
+* ``CSMCState``, ``Distribution``, ``UnivariatePotential``, ``Dynamics``, ``Potential``
+  (aux_samplers/_primitives/csmc/base.py:18-71)
+* ``get_kernel(M0, G0, Mt, Gt, N, backward=False, Pt=None)`` -> ``(init, kernel)``; ``kernel(key, state)``
+  (aux_samplers/_primitives/csmc/csmc.py:16-66)
+* ``get_generic_kernel(factory, N, backward=False, Pt=None)`` -> ``kernel(key, state, delta)``
+  (aux_samplers/csmc/generic.py:14-79; raises ValueError when ``backward`` without ``Pt``, :44-47)
+* ``get_independent_kernel(M0, G0, Mt, Gt, N, backward=False, Pt=None, gradient=False, parallel=False)``
+  (aux_samplers/csmc/independent.py:18-75)
+* unfused primitives ``normalize``, ``multinomial``, ``killing``, ``categorical``
+  (math/utils.py:24-39, resamplings.py:14-37, csmc.py:111)
+
+The reference calls user Python callables inside its time loop.  A fused CUDA sweep cannot, so the
+model pieces are *descriptors* from a closed family set (see include/auxssm.h): a linear-Gaussian
+prior (``GaussianDistribution`` + ``LinearGaussianDynamics``) with a ``Flat`` / ``GaussianObservation`` /
+``StochasticVolatility`` potential, proposed from the prior (bootstrap), from the independent auxiliary
+proposal, or from the guided auxiliary proposal.  Anything else raises ``NotImplementedError`` and
+must be written against the unfused primitives.
+
+``state.x`` is ``[C, T, d]`` (chains leading) or ``[T, d]``.  ``key`` is a draws object (``draws.py``);
+call order: normals ``[C,T,d]`` (auxiliary kernels only), normals ``[C,T,N,d]``, uniforms ``[C,T-1,N]``,
+(killing: uniforms ``[C,T-1,N]``), uniforms ``[C,T]``.
+"""
+import ctypes
+from typing import NamedTuple, Optional
+
+import torch
+
+from . import _lib
+from ._lib import AuxssmError, CsmcDesc
+
+
+class CSMCState(NamedTuple):
+    x: torch.Tensor
+    updated: torch.Tensor
+
+
+# ---- model-family descriptors (mirroring csmc/base.py's abstract classes) -------------------------
+
+class Distribution:
+    pass
+
+
+class UnivariatePotential:
+    pass
+
+
+class Dynamics:
+    params = None
+
+
+class Potential:
+    params = None
+
+
+class GaussianDistribution(Distribution, UnivariatePotential):
+    """x_0 ~ N(m0, P0) (the role of ``M0`` in auxiliary_csmc.py:25-31)."""
+
+    def __init__(self, m0, P0):
+        self.m0, self.P0 = m0, P0
+        self.chol_P0 = torch.linalg.cholesky(P0) if P0.shape[-1] > 1 else torch.sqrt(P0)
+
+    def logpdf(self, x):  # presence of this attribute is what the reference checks (csmc.py:49)
+        raise NotImplementedError("evaluated inside the fused kernel")
+
+
+class LinearGaussianDynamics(Dynamics):
+    """x_t ~ N(F x_{t-1} + b, Q), time-invariant (``Mt`` of auxiliary_csmc.py:33-40; ``GaussianDynamics(rho)``
+    of the reference's tests is F = rho, Q = 1 - rho^2, b = 0)."""
+
+    def __init__(self, F, Q, b):
+        self.F, self.Q, self.b = F, Q, b
+        self.chol_Q = torch.linalg.cholesky(Q) if Q.shape[-1] > 1 else torch.sqrt(Q)
+
+    def logpdf(self, x_t_p_1, x_t, params):
+        raise NotImplementedError("evaluated inside the fused kernel")
+
+
+class FlatPotential(Potential, UnivariatePotential):
+    """test_csmc/common.py:67-81."""
+    kind = _lib.POT_FLAT
+    ys, sig = None, 1.0
+
+
+class GaussianObservationPotential(Potential, UnivariatePotential):
+    """sum_i log N(y_ti; x_i, sig)  (test_csmc/common.py:57-63); ``ys`` is [T, d] (or [C, T, d])."""
+    kind = _lib.POT_GAUSSIAN
+
+    def __init__(self, ys, sig=1.0):
+        self.ys, self.sig = ys, float(sig)
+
+
+class StochasticVolatilityPotential(Potential, UnivariatePotential):
+    """sum_i log N(y_ti; 0, exp(x_i / 2))  (auxiliary_csmc.py:41-46)."""
+    kind = _lib.POT_SV
+    sig = 1.0
+
+    def __init__(self, ys):
+        self.ys = ys
+
+
+class _Aux(NamedTuple):
+    proposal: int
+    u: torch.Tensor
+    sqrt_half_delta: torch.Tensor
+    grad: Optional[torch.Tensor]
+    gradient: bool
+    K: Optional[torch.Tensor]
+    chol_Lam: Optional[torch.Tensor]
+
+
+class AuxiliaryFeynmanKac(NamedTuple):
+    """What a ``factory(u, sqrt_half_delta)`` returns in place of the reference's four JAX callables."""
+    M0: GaussianDistribution
+    G0: UnivariatePotential
+    Mt: LinearGaussianDynamics
+    Gt: Potential
+    aux: _Aux
+
+    def __iter__(self):  # so that ``m0, g0, mt, gt = factory(...)`` keeps working
+        return iter((self.M0, self.G0, self.Mt, self.Gt))
+
+
+def _check_family(M0, G0, Mt, Gt):
+    if not isinstance(M0, GaussianDistribution) or not isinstance(Mt, LinearGaussianDynamics):
+        raise NotImplementedError(
+            "the fused cSMC sweep supports GaussianDistribution / LinearGaussianDynamics priors only; "
+            "use the unfused primitives (normalize, multinomial, killing, categorical) for other models")
+    for g in (G0, Gt):
+        if not hasattr(g, "kind"):
+            raise NotImplementedError("unsupported potential %r (closed family set, see include/auxssm.h)" % (g,))
+    if G0.kind != Gt.kind:
+        raise NotImplementedError("G0 and Gt must be the same potential family")
+    return Gt
+
+
+def _sweep(x_star, M0, Mt, pot, N, backward, resampling, key, aux=None, return_history=False):
+    squeeze = x_star.dim() == 2
+    x = x_star.unsqueeze(0) if squeeze else x_star
+    x = x.contiguous()
+    dev = _lib.require_cuda(x)
+    dtype = x.dtype
+    sfx = _lib.suffix(dtype)
+    C, T, d = x.shape
+    desc = CsmcDesc()
+    desc.T, desc.N, desc.d, desc.n_chains = T, N, d, C
+    desc.proposal = aux.proposal if aux is not None else _lib.PROP_BOOTSTRAP
+    desc.potential = pot.kind
+    desc.resampling = {"multinomial": _lib.RESAMPLE_MULTINOMIAL, "killing": _lib.RESAMPLE_KILLING}[resampling]
+    desc.backward = 1 if backward else 0
+    desc.gradient = 1 if (aux is not None and aux.gradient) else 0
+    desc.sig = float(pot.sig)
+    ys = None
+    if pot.ys is not None:
+        ys = pot.ys.to(dtype).contiguous()
+        desc.ys_chain_stride = 0 if ys.dim() == 2 else T * d
+    cvt = lambda t: None if t is None else t.to(device=dev, dtype=dtype).contiguous()
+    u = shd = grad = K = cL = None
+    if aux is not None:
+        u, shd, grad, K, cL = cvt(aux.u), cvt(aux.sqrt_half_delta), cvt(aux.grad), cvt(aux.K), cvt(aux.chol_Lam)
+        desc.gains_time_stride = 0 if (K is None or K.dim() == 2) else d * d
+    normals = key.normal((C, T, N, d), dtype, dev).contiguous()
+    u_res = key.uniform((C, max(T - 1, 0), N), dtype, dev).contiguous()
+    u_kill = key.uniform((C, max(T - 1, 0), N), dtype, dev).contiguous() if resampling == "killing" else None
+    u_bwd = key.uniform((C, T), dtype, dev).contiguous()
+    x_out = torch.empty_like(x)
+    anc = torch.empty((C, T), dtype=torch.int32, device=dev)
+    xs_h = lw_h = a_h = None
+    scratch = None
+    L = _lib.lib()
+    if return_history:
+        xs_h = torch.empty((C, T, N, d), dtype=dtype, device=dev)
+        lw_h = torch.empty((C, T, N), dtype=dtype, device=dev)
+        a_h = torch.empty((C, max(T - 1, 0), N), dtype=torch.int32, device=dev)
+        nbytes = 0
+    else:
+        nbytes = L.auxssm_csmc_scratch_bytes(desc, x.element_size())
+        scratch = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+    _lib.call("auxssm_csmc_sweep_" + sfx, _lib.stream_ptr(dev), desc, _lib.ptr(x), _lib.ptr(cvt(M0.m0)),
+              _lib.ptr(cvt(M0.chol_P0)), _lib.ptr(cvt(Mt.F)), _lib.ptr(cvt(Mt.b)), _lib.ptr(cvt(Mt.chol_Q)),
+              _lib.ptr(ys), _lib.ptr(u), _lib.ptr(shd), _lib.ptr(grad), _lib.ptr(K), _lib.ptr(cL),
+              _lib.ptr(normals), _lib.ptr(u_res), _lib.ptr(u_kill), _lib.ptr(u_bwd), _lib.ptr(x_out), _lib.ptr(anc),
+              _lib.ptr(xs_h), _lib.ptr(lw_h), _lib.ptr(a_h), _lib.ptr(scratch), int(nbytes))
+    updated = anc != 0
+    if squeeze:
+        x_out, updated, anc = x_out[0], updated[0], anc[0]
+    state = CSMCState(x=x_out, updated=updated)
+    if return_history:
+        return state, dict(ancestors=anc, xs=xs_h, log_ws=lw_h, As=a_h)
+    return state
+
+
+def get_kernel(M0, G0, Mt, Gt, N, backward=False, Pt=None, *, resampling="multinomial", _aux=None,
+               return_history=False):
+    """cSMC kernel of csmc.py:16-66: returns ``(init, kernel)``; ``kernel(key, state) -> CSMCState``."""
+    if backward and Pt is None:
+        Pt = Mt
+    elif backward and not hasattr(Pt, "logpdf"):
+        raise ValueError("When `backward` is True, `Pt` must implement a valid logpdf method.")
+    pot = _check_family(M0, G0, Mt, Gt)
+    if backward and Pt is not Mt and not (isinstance(Pt, LinearGaussianDynamics) and Pt.F is Mt.F and Pt.Q is Mt.Q):
+        raise NotImplementedError("backward sampling uses the prior transition of the fused family (Pt must be Mt)")
+
+    def kernel(key, state):
+        return _sweep(state.x, M0, Mt, pot, N, backward, resampling, key, _aux, return_history)
+
+    def init(x_star):
+        T = x_star.shape[-2]
+        shape = x_star.shape[:-2] + (T,)
+        return CSMCState(x=x_star, updated=torch.ones(shape, dtype=torch.bool, device=x_star.device))
+
+    return init, kernel
+
+
+def _aux_u(key, x, delta):
+    """u = x + sqrt(delta_t / 2) eps with per-time-step delta (csmc/generic.py:61-67)."""
+    from .kalman import auxiliary_draw
+    C, T, d = x.shape
+    dl = torch.as_tensor(delta, dtype=x.dtype, device=x.device)
+    dl = dl.expand(T) if dl.dim() == 0 else dl
+    dl = dl.expand(C, T).contiguous() if dl.dim() == 1 else dl.contiguous()
+    eps = key.normal((C, T, d), x.dtype, x.device)
+    u = auxiliary_draw(x.reshape(C * T, d), eps.reshape(C * T, d), dl.reshape(C * T)).reshape(C, T, d)
+    return u, torch.sqrt(0.5 * dl)
+
+
+def get_generic_kernel(factory, N, backward=False, Pt=None, *, resampling="multinomial", return_history=False):
+    """Auxiliary particle Gibbs with generic proposals (csmc/generic.py:14-79).
+
+    ``factory(u [C,T,d], sqrt_half_delta [C,T]) -> AuxiliaryFeynmanKac`` (see ``independent_factory`` and
+    ``stochastic_volatility.guided_factory``).  ``kernel(key, state, delta)``; ``delta`` scalar, ``[T]`` or ``[C,T]``.
+    """
+    if backward and Pt is None:
+        raise ValueError("If backward is True, the true dynamics `Pt` must be provided.")
+    elif backward and not hasattr(Pt, "logpdf"):
+        raise ValueError("`Pt` must implement a valid logpdf method.")
+
+    def kernel(key, state, delta):
+        x = state.x
+        squeeze = x.dim() == 2
+        xb = (x.unsqueeze(0) if squeeze else x).contiguous()
+        u, shd = _aux_u(key, xb, delta)
+        fk = factory(u, shd)
+        if not isinstance(fk, AuxiliaryFeynmanKac):
+            raise NotImplementedError("factory must return an AuxiliaryFeynmanKac from the closed family set")
+        _, inner = get_kernel(fk.M0, fk.G0, fk.Mt, fk.Gt, N, backward, Pt, resampling=resampling, _aux=fk.aux,
+                              return_history=return_history)
+        out = inner(key, CSMCState(xb, state.updated))
+        if squeeze:
+            if return_history:
+                st, h = out
+                return CSMCState(st.x[0], st.updated[0]), h
+            return CSMCState(out.x[0], out.updated[0])
+        return out
+
+    def init(x):
+        T = x.shape[-2]
+        return CSMCState(x=x, updated=torch.zeros(x.shape[:-2] + (T,), dtype=torch.bool, device=x.device))
+
+    return init, kernel
+
+
+def grad_log_target(u, M0, G0, Mt, Gt):
+    """Gradient at ``u`` [C,T,d] of log M0(u_0) + G0(u_0) + sum_t (Gt(u_t) + log Mt(u_t | u_{t-1})), the quantity
+    the reference obtains with ``jax.grad(_log_pdf)`` (independent.py:62,121-137); analytic for the closed
+    family set.  Host-side proposal construction (torch), not part of the fused sweep."""
+    pot = _check_family(M0, G0, Mt, Gt)
+    F, b = Mt.F.to(u), Mt.b.to(u)
+    r0 = torch.cholesky_solve((u[:, 0] - M0.m0.to(u)).unsqueeze(-1), M0.chol_P0.to(u)).squeeze(-1)
+    res = u[:, 1:] - (u[:, :-1] @ F.T + b)
+    rt = torch.cholesky_solve(res.unsqueeze(-1), Mt.chol_Q.to(u)).squeeze(-1)
+    grad = torch.zeros_like(u)
+    grad[:, 0] -= r0
+    grad[:, 1:] -= rt
+    grad[:, :-1] += rt @ F
+    if pot.kind == _lib.POT_GAUSSIAN:
+        grad += (pot.ys.to(u) - u) / pot.sig ** 2
+    elif pot.kind == _lib.POT_SV:
+        y = pot.ys.to(u)
+        grad += 0.5 * y * y * torch.exp(-u) - 0.5
+    return grad
+
+
+def independent_factory(M0, G0, Mt, Gt, gradient=False):
+    """``factory`` of independent.py:60-73: proposal N(u_t + (delta_t/2) grad_t, (delta_t/2) I)."""
+    _check_family(M0, G0, Mt, Gt)
+
+    def factory(u, scale):
+        grad = grad_log_target(u, M0, G0, Mt, Gt) if gradient else None
+        return AuxiliaryFeynmanKac(M0, G0, Mt, Gt, _Aux(_lib.PROP_INDEPENDENT, u, scale, grad, gradient, None, None))
+
+    return factory
+
+
+def get_independent_kernel(M0, G0, Mt, Gt, N, backward=False, Pt=None, gradient=False, parallel=False, *,
+                           resampling="multinomial", return_history=False):
+    """Auxiliary particle Gibbs with independent (separable) proposals (independent.py:18-75)."""
+    if parallel:
+        raise NotImplementedError("parallel-in-time cSMC (independent.py:78-118, _primitives/csmc/pit) is out of "
+                                  "scope of this build (SURVEY section 8(f), rank 3)")
+    return get_generic_kernel(independent_factory(M0, G0, Mt, Gt, gradient), N, backward, Pt,
+                              resampling=resampling, return_history=return_history)
+
+
+def guided_gains(P0, Q, sqrt_half_delta):
+    """K_t, chol(Lambda_t) for every t (auxiliary_guided_csmc.py:155-157, :44-46); sqrt_half_delta is [T]."""
+    dev = _lib.require_cuda(P0, Q, sqrt_half_delta)
+    sfx = _lib.suffix(P0.dtype)
+    T, d = sqrt_half_delta.shape[0], P0.shape[-1]
+    K = torch.empty((T, d, d), dtype=P0.dtype, device=dev)
+    cL = torch.empty_like(K)
+    _lib.call("auxssm_guided_gains_" + sfx, _lib.stream_ptr(dev), T, d, _lib.ptr(P0.contiguous()),
+              _lib.ptr(Q.contiguous()), _lib.ptr(sqrt_half_delta.contiguous()), _lib.ptr(K), _lib.ptr(cL))
+    return K, cL
+
+
+def guided_factory(M0, G0, Mt, Gt):
+    """``factory`` of auxiliary_guided_csmc.py:19-24 (``grad=False``).  Requires delta shared by all chains."""
+    _check_family(M0, G0, Mt, Gt)
+
+    def factory(u, scale):
+        K, cL = guided_gains(M0.P0.to(u), Mt.Q.to(u), scale[0].contiguous())
+        return AuxiliaryFeynmanKac(M0, G0, Mt, Gt, _Aux(_lib.PROP_GUIDED, u, scale, None, False, K, cL))
+
+    return factory
+
+
+# ---- unfused primitives -----------------------------------------------------------------------------
+
+def _rows(t):
+    return t.reshape(-1, t.shape[-1]).contiguous()
+
+
+def normalize(log_weights):
+    """exp(lw - logsumexp(lw)) over the last axis (math/utils.py:24-39)."""
+    dev = _lib.require_cuda(log_weights)
+    lw = _rows(log_weights)
+    w = torch.empty_like(lw)
+    _lib.call("auxssm_normalize_" + _lib.suffix(lw.dtype), _lib.stream_ptr(dev), lw.shape[0], lw.shape[1],
+              _lib.ptr(lw), _lib.ptr(w))
+    return w.reshape(log_weights.shape)
+
+
+def multinomial(uniforms, weights):
+    """Conditional multinomial resampling (resamplings.py:14-37) with supplied uniforms [..., N]."""
+    dev = _lib.require_cuda(weights, uniforms)
+    w, u = _rows(weights), _rows(uniforms)
+    idx = torch.empty(w.shape, dtype=torch.int32, device=dev)
+    _lib.call("auxssm_resample_multinomial_" + _lib.suffix(w.dtype), _lib.stream_ptr(dev), w.shape[0], w.shape[1],
+              _lib.ptr(w), _lib.ptr(u), _lib.ptr(idx))
+    return idx.reshape(weights.shape)
+
+
+def killing(uniforms_kill, uniforms, weights):
+    """Conditional killing resampling (not in the reference; spec in oracle/csmc.py)."""
+    dev = _lib.require_cuda(weights, uniforms, uniforms_kill)
+    w, u, uk = _rows(weights), _rows(uniforms), _rows(uniforms_kill)
+    idx = torch.empty(w.shape, dtype=torch.int32, device=dev)
+    _lib.call("auxssm_resample_killing_" + _lib.suffix(w.dtype), _lib.stream_ptr(dev), w.shape[0], w.shape[1],
+              _lib.ptr(w), _lib.ptr(uk), _lib.ptr(u), _lib.ptr(idx))
+    return idx.reshape(weights.shape)
+
+
+def categorical(uniforms, weights):
+    """One ``jax.random.choice(key, N, p=w, shape=())`` draw per row; uniforms [...], weights [..., N]."""
+    dev = _lib.require_cuda(weights, uniforms)
+    w = _rows(weights)
+    u = uniforms.reshape(-1).contiguous()
+    idx = torch.empty((w.shape[0],), dtype=torch.int32, device=dev)
+    _lib.call("auxssm_categorical_" + _lib.suffix(w.dtype), _lib.stream_ptr(dev), w.shape[0], w.shape[1],
+              _lib.ptr(w), _lib.ptr(u), _lib.ptr(idx))
+    return idx.reshape(weights.shape[:-1])

@@ -1,0 +1,48 @@
+// Host-side dispatch of the fused cSMC sweep on (D, MAXT) for one proposal family; each family is
+// instantiated in its own translation unit so the families compile in parallel.
+#pragma once
+#include "csmc_kernel.cuh"
+
+namespace auxssm {
+
+template <typename T, int PROP> int launch_csmc_family(cudaStream_t st, CsmcArgs<T>& a, int max_slots, int* slots_used);
+
+template <typename T, int D, int PROP, int MAXT>
+static int launch_csmc_one(cudaStream_t st, CsmcArgs<T>& a, int max_slots, int* slots_used) {
+  const int N = a.d.N;
+  const int ntb = (N + 31) / 32 * 32;
+  const size_t smem = csmc_smem_elems<D>(N, a.d.d, PROP) * sizeof(T);
+  auto kern = csmc_sweep_kernel<T, D, PROP, MAXT>;
+  int rc = ensure_smem(kern, smem, "auxssm_csmc_sweep");
+  if (rc) return rc;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ntb, smem);
+  if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+  long grid = (long)per_sm * device_sm_count();
+  if (grid > a.d.n_chains) grid = a.d.n_chains;
+  if (!a.hist_per_chain && grid > max_slots) grid = max_slots;
+  if (grid < 1) grid = 1;
+  if (slots_used) *slots_used = (int)grid;
+  if (st == (cudaStream_t)-1) return AUXSSM_OK;  // planning only
+  kern<<<(unsigned)grid, ntb, smem, st>>>(a);
+  AUXSSM_CHECK_LAUNCH("auxssm_csmc_sweep");
+  return AUXSSM_OK;
+}
+
+template <typename T, int PROP>
+int launch_csmc_family(cudaStream_t st, CsmcArgs<T>& a, int max_slots, int* slots_used) {
+  const int d = a.d.d, N = a.d.N;
+  const bool big = N > 256;
+#define AUXSSM_CSMC_CASE(DD)                                                                  \
+  return big ? launch_csmc_one<T, DD, PROP, 1024>(st, a, max_slots, slots_used)               \
+             : launch_csmc_one<T, DD, PROP, 256>(st, a, max_slots, slots_used)
+  if (d <= 1) { AUXSSM_CSMC_CASE(1); }
+  if (d <= 4) { AUXSSM_CSMC_CASE(4); }
+  if (d <= 8) { AUXSSM_CSMC_CASE(8); }
+  if (d <= 32) { AUXSSM_CSMC_CASE(32); }
+#undef AUXSSM_CSMC_CASE
+  set_error("auxssm_csmc_sweep: d = %d exceeds 32", d);
+  return AUXSSM_ERR_UNSUPPORTED;
+}
+
+}  // namespace auxssm

@@ -165,6 +165,90 @@ int32_t auxssm_sv_log_potential_f32(void* stream, int64_t n_chains, int64_t n_pe
 int32_t auxssm_sv_log_potential_f64(void* stream, int64_t n_chains, int64_t n_per_chain, const double* ys,
                                     int64_t ys_chain_stride, const double* x, double* out, int32_t accumulate);
 
+/* ---- Conditional SMC particle Gibbs sweep: replaces _primitives/csmc/csmc.py:16-149 ---------------
+ * (get_kernel/kernel :16-66, _csmc :69-107, _backward_scanning_pass :110-124,
+ * _backward_sampling_pass :127-149), the conditional resamplers of resamplings.py:14-37, normalize
+ * (math/utils.py:24-39) and the auxiliary wrappers csmc/generic.py:56-72, csmc/independent.py:144-268,
+ * examples/stochastic_volatility/auxiliary_guided_csmc.py:29-167.
+ *
+ * The reference calls user Python callables (M0.sample, G0, Mt.sample, Gt, Pt.logpdf) inside the time
+ * loop; a fused kernel needs a closed set of model families instead:
+ *   prior      x_0 ~ N(m0, P0),  x_t ~ N(F x_{t-1} + b, Q)   (time-invariant, chol factors supplied)
+ *   potential  FLAT 0 | GAUSSIAN sum_i log N(y_ti; x_i, sig) | SV sum_i log N(y_ti; 0, exp(x_i/2))
+ *   proposal   BOOTSTRAP    propose from the prior, weight = potential
+ *              INDEPENDENT  N(u_t + s_t^2 grad_t, s_t^2 I), weight = log prior transition + potential
+ *                           (+ log N(x;u,s) - log N(x;mean,s) when `gradient`)      independent.py:144-268
+ *              GUIDED       N(mu_t, Lambda_t), mu_t = xpred + K_t (u_t - xpred); K_t, chol Lambda_t from
+ *                           auxssm_guided_gains_*                        auxiliary_guided_csmc.py:90-167
+ * Anything else must use the unfused primitives below, one call per time step.
+ *
+ * Draws are inputs (parity mode): normals[n_chains,T,N,d] (csmc.py:74,91), u_resample[n_chains,T-1,N]
+ * (resamplings.py:35), u_kill[n_chains,T-1,N] (killing only), u_backward[n_chains,T] (csmc.py:111 /
+ * :131,138).  Categorical draws follow jax.random.choice: idx = first j with cdf[j] >= cdf[N-1](1-U),
+ * with the CDF accumulated in the library's canonical order.
+ * Outputs: x_out[n_chains,T,d], ancestors[n_chains,T] (updated = ancestors != 0, csmc.py:59).
+ * Optional (may be NULL) full history: xs_hist[n_chains,T,N,d], logw_hist[n_chains,T,N],
+ * anc_hist[n_chains,T-1,N].  N <= 1024, d <= 32.                                                      */
+enum { AUXSSM_PROP_BOOTSTRAP = 0, AUXSSM_PROP_INDEPENDENT = 1, AUXSSM_PROP_GUIDED = 2 };
+enum { AUXSSM_POT_FLAT = 0, AUXSSM_POT_GAUSSIAN = 1, AUXSSM_POT_SV = 2 };
+enum { AUXSSM_RESAMPLE_MULTINOMIAL = 0, AUXSSM_RESAMPLE_KILLING = 1 };
+
+typedef struct auxssm_csmc_desc {
+  int32_t T, N, d, n_chains;
+  int32_t proposal, potential, resampling;
+  int32_t backward;         /* 0: ancestor tracing; 1: backward sampling with Pt = the prior transition */
+  int32_t gradient;         /* INDEPENDENT only: weights carry the gradient correction                   */
+  int64_t ys_chain_stride;  /* 0: one data set ys[T,d] shared by all chains; T*d: one per chain          */
+  int64_t gains_time_stride;/* GUIDED: d*d if K / cholLam are [T,d,d], 0 if time-invariant [d,d]         */
+  double sig;               /* GAUSSIAN potential: observation std                                       */
+} auxssm_csmc_desc;
+
+size_t auxssm_csmc_scratch_bytes(const auxssm_csmc_desc* desc, int32_t elem_size);
+int32_t auxssm_csmc_sweep_f32(void* stream, const auxssm_csmc_desc* desc, const float* x_star,
+                              const float* m0, const float* chol_P0, const float* F, const float* b,
+                              const float* chol_Q, const float* ys, const float* u, const float* sqrt_half_delta,
+                              const float* grad, const float* K, const float* chol_Lam, const float* normals,
+                              const float* u_resample, const float* u_kill, const float* u_backward,
+                              float* x_out, int32_t* ancestors, float* xs_hist, float* logw_hist,
+                              int32_t* anc_hist, void* scratch, size_t scratch_bytes);
+int32_t auxssm_csmc_sweep_f64(void* stream, const auxssm_csmc_desc* desc, const double* x_star,
+                              const double* m0, const double* chol_P0, const double* F, const double* b,
+                              const double* chol_Q, const double* ys, const double* u,
+                              const double* sqrt_half_delta, const double* grad, const double* K,
+                              const double* chol_Lam, const double* normals, const double* u_resample,
+                              const double* u_kill, const double* u_backward, double* x_out, int32_t* ancestors,
+                              double* xs_hist, double* logw_hist, int32_t* anc_hist, void* scratch,
+                              size_t scratch_bytes);
+
+/* Gains of the guided proposal for every time step (auxiliary_guided_csmc.py:155-157, :44-46, :104-106):
+ * K_t = P (P + s_t^2 I)^{-1}, chol_Lam_t = chol(sym(P - K_t P)) with non-finite entries replaced by
+ * s_t I; P = P0 for t = 0 and Q otherwise.  sqrt_half_delta[T]; outputs [T,d,d].                       */
+int32_t auxssm_guided_gains_f32(void* stream, int32_t T, int32_t d, const float* P0, const float* Q,
+                                const float* sqrt_half_delta, float* K, float* chol_Lam);
+int32_t auxssm_guided_gains_f64(void* stream, int32_t T, int32_t d, const double* P0, const double* Q,
+                                const double* sqrt_half_delta, double* K, double* chol_Lam);
+
+/* ---- Unfused cSMC primitives (for models outside the closed set), rows are independent ------------
+ * normalize      w = exp(lw - logsumexp(lw))                                   math/utils.py:24-39
+ * multinomial    idx[r, :] conditional multinomial, idx[r, 0] = 0              resamplings.py:14-37
+ * killing        idx = i if u_kill * max w < w_i else multinomial draw; idx[r, 0] = 0  (not in the reference)
+ * categorical    one draw per row: jax.random.choice(key, N, p=w, shape=())    csmc.py:111,131,138
+ * Arrays are [n_rows, N] contiguous, N <= 1024.                                                       */
+int32_t auxssm_normalize_f32(void* stream, int64_t n_rows, int32_t N, const float* log_w, float* w);
+int32_t auxssm_normalize_f64(void* stream, int64_t n_rows, int32_t N, const double* log_w, double* w);
+int32_t auxssm_resample_multinomial_f32(void* stream, int64_t n_rows, int32_t N, const float* w,
+                                        const float* u, int32_t* idx);
+int32_t auxssm_resample_multinomial_f64(void* stream, int64_t n_rows, int32_t N, const double* w,
+                                        const double* u, int32_t* idx);
+int32_t auxssm_resample_killing_f32(void* stream, int64_t n_rows, int32_t N, const float* w,
+                                    const float* u_kill, const float* u, int32_t* idx);
+int32_t auxssm_resample_killing_f64(void* stream, int64_t n_rows, int32_t N, const double* w,
+                                    const double* u_kill, const double* u, int32_t* idx);
+int32_t auxssm_categorical_f32(void* stream, int64_t n_rows, int32_t N, const float* w, const float* u,
+                               int32_t* idx);
+int32_t auxssm_categorical_f64(void* stream, int64_t n_rows, int32_t N, const double* w, const double* u,
+                               int32_t* idx);
+
 #ifdef __cplusplus
 }
 #endif

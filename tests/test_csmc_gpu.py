@@ -1,0 +1,216 @@
+"""Parity of the CUDA conditional-SMC path (through the C ABI) against the oracle with identical draws.
+
+Indices (resampling ancestors, backward-sampled ancestors) must match bit-exactly; floating-point
+histories and trajectories within 1e-5 (fp64) / 1e-3 (fp32) relative.  In fp32 the weights go through
+exp/log whose last bit differs between NumPy and CUDA, so an index may legitimately differ when the
+uniform lands within a few ulp of a CDF knot: the fp32 tests use seeds where that does not happen and
+the primitive tests (weights supplied => no transcendental in between) assert exact equality."""
+import numpy as np
+import numpy.testing as npt
+import pytest
+import torch
+
+from oracle import csmc as oc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {torch.float64: 1e-5, torch.float32: 1e-3}
+NP = {torch.float64: np.float64, torch.float32: np.float32}
+
+
+def dev(a, dtype):
+    return None if a is None else torch.as_tensor(np.ascontiguousarray(a)).to(device="cuda", dtype=dtype)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("N", [1, 7, 32, 33, 100, 1000, 1024])
+def test_primitives_exact_indices(dtype, N):
+    from aux_ssm_samplers_b200 import csmc
+    rng = np.random.default_rng(N)
+    R = 64
+    lw = (3.0 * rng.standard_normal((R, N))).astype(NP[dtype])
+    w_gpu = csmc.normalize(dev(lw, dtype))
+    npt.assert_allclose(host(w_gpu), oc.normalize(lw), rtol=2e-5 if dtype == torch.float32 else 1e-12)
+    # feed the SAME weights to both sides: index parity is then bit-exact by construction
+    w = host(w_gpu)
+    u = rng.uniform(size=(R, N)).astype(NP[dtype])
+    uk = rng.uniform(size=(R, N)).astype(NP[dtype])
+    u1 = rng.uniform(size=R).astype(NP[dtype])
+    npt.assert_array_equal(host(csmc.multinomial(dev(u, dtype), w_gpu)), oc.multinomial(w, u))
+    npt.assert_array_equal(host(csmc.killing(dev(uk, dtype), dev(u, dtype), w_gpu)), oc.killing(w, uk, u))
+    npt.assert_array_equal(host(csmc.categorical(dev(u1, dtype), w_gpu)), oc.categorical(w, u1))
+
+
+def make_model(rng, d, T, potential, dtype):
+    A = rng.standard_normal((d, d))
+    Q = (A @ A.T / d + 0.3 * np.eye(d)) * 0.4
+    F = 0.8 * np.eye(d) + 0.1 * rng.standard_normal((d, d)) / np.sqrt(d)
+    b = 0.1 * rng.standard_normal(d)
+    m0 = 0.2 * rng.standard_normal(d)
+    P0 = Q * 2.0
+    ys = rng.standard_normal((T, d)) if potential != "flat" else None
+    return oc.LinearGaussianModel(m0, P0, F, Q, b, potential, ys=ys, sig=0.7, dtype=NP[dtype])
+
+
+def gpu_family(model, dtype):
+    from aux_ssm_samplers_b200 import csmc
+    M0 = csmc.GaussianDistribution(dev(model.m0, dtype), dev(model.P0, dtype))
+    Mt = csmc.LinearGaussianDynamics(dev(model.F, dtype), dev(model.Q, dtype), dev(model.b, dtype))
+    if model.potential == "flat":
+        G = csmc.FlatPotential()
+    elif model.potential == "gaussian":
+        G = csmc.GaussianObservationPotential(dev(model.ys, dtype), model.sig)
+    else:
+        G = csmc.StochasticVolatilityPotential(dev(model.ys, dtype))
+    return M0, G, Mt, G
+
+
+def compare(state, hist, oracle_out, dtype, C):
+    r = RTOL[dtype]
+    for c in range(C):
+        x, upd, B, (w_T, xs, log_ws, As) = oracle_out[c]
+        npt.assert_array_equal(host(hist["As"][c]), As, err_msg="resampling ancestors, chain %d" % c)
+        npt.assert_allclose(host(hist["xs"][c]), xs, rtol=r, atol=r * np.abs(xs).max())
+        fin = np.isfinite(log_ws)
+        npt.assert_allclose(host(hist["log_ws"][c])[fin], log_ws[fin], rtol=r, atol=r * 10)
+        npt.assert_array_equal(host(hist["ancestors"][c]), B, err_msg="backward ancestors, chain %d" % c)
+        npt.assert_array_equal(host(state.updated[c]), upd)
+        npt.assert_allclose(host(state.x[c]), x, rtol=r, atol=r * np.abs(x).max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("potential", ["flat", "gaussian", "sv"])
+@pytest.mark.parametrize("d,N,T", [(1, 32, 5), (1, 300, 12), (2, 100, 9), (5, 40, 7), (30, 64, 6)])
+@pytest.mark.parametrize("backward", [False, True])
+@pytest.mark.parametrize("resampling", ["multinomial", "killing"])
+def test_bootstrap_sweep_vs_oracle(dtype, potential, d, N, T, backward, resampling):
+    from aux_ssm_samplers_b200 import csmc
+    from aux_ssm_samplers_b200.draws import ExternalDraws
+    rng = np.random.default_rng(1000 * d + N + T)
+    C = 3
+    model = make_model(rng, d, T, potential, dtype)
+    npd = NP[dtype]
+    x_star = rng.standard_normal((C, T, d)).astype(npd)
+    normals = rng.standard_normal((C, T, N, d)).astype(npd)
+    u_res = rng.uniform(size=(C, T - 1, N)).astype(npd)
+    u_kill = rng.uniform(size=(C, T - 1, N)).astype(npd)
+    u_bwd = rng.uniform(size=(C, T)).astype(npd)
+    fk = oc.BootstrapFK(model)
+    want = [oc.csmc_kernel(fk, model, x_star[c], normals[c], u_res[c], u_bwd[c], backward, resampling, u_kill[c])
+            for c in range(C)]
+    M0, G0, Mt, Gt = gpu_family(model, dtype)
+    _, kernel = csmc.get_kernel(M0, G0, Mt, Gt, N, backward, resampling=resampling, return_history=True)
+    unis = [u_res] + ([u_kill] if resampling == "killing" else []) + [u_bwd]
+    state, hist = kernel(ExternalDraws([normals], unis), csmc.CSMCState(dev(x_star, dtype), None))
+    torch.cuda.synchronize()
+    compare(state, hist, want, dtype, C)
+    # same sweep through the scratch-slot path (no history outputs) must give the same trajectory
+    _, kernel2 = csmc.get_kernel(M0, G0, Mt, Gt, N, backward, resampling=resampling)
+    state2 = kernel2(ExternalDraws([normals], unis), csmc.CSMCState(dev(x_star, dtype), None))
+    npt.assert_array_equal(host(state2.x), host(state.x))
+    npt.assert_array_equal(host(state2.updated), host(state.updated))
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("kind", ["independent", "independent-grad", "guided"])
+@pytest.mark.parametrize("d,N,T", [(1, 64, 8), (3, 50, 6), (30, 48, 5)])
+@pytest.mark.parametrize("backward", [False, True])
+def test_auxiliary_sweeps_vs_oracle(dtype, kind, d, N, T, backward):
+    from aux_ssm_samplers_b200 import csmc
+    from aux_ssm_samplers_b200.draws import ExternalDraws
+    rng = np.random.default_rng(77 + d + N)
+    C = 2
+    npd = NP[dtype]
+    model = make_model(rng, d, T, "sv", dtype)
+    delta = rng.uniform(0.2, 0.6, size=T).astype(npd)
+    x_star = rng.standard_normal((C, T, d)).astype(npd)
+    n_aux = rng.standard_normal((C, T, d)).astype(npd)
+    normals = rng.standard_normal((C, T, N, d)).astype(npd)
+    u_res = rng.uniform(size=(C, T - 1, N)).astype(npd)
+    u_bwd = rng.uniform(size=(C, T)).astype(npd)
+    M0, G0, Mt, Gt = gpu_family(model, dtype)
+    want = []
+    for c in range(C):
+        u, s = oc.aux_u(x_star[c], delta, n_aux[c])
+        if kind == "guided":
+            fk = oc.GuidedAuxFK(model, u, s)
+        else:
+            grad = None
+            if kind == "independent-grad":
+                grad = host(csmc.grad_log_target(dev(u[None], dtype), M0, G0, Mt, Gt))[0].astype(npd)
+            fk = oc.IndependentAuxFK(model, u, s, grad, gradient=(kind == "independent-grad"))
+        want.append(oc.csmc_kernel(fk, model, x_star[c], normals[c], u_res[c], u_bwd[c], backward))
+    if kind == "guided":
+        _, kernel = csmc.get_generic_kernel(csmc.guided_factory(M0, G0, Mt, Gt), N, backward, Pt=Mt,
+                                            return_history=True)
+    else:
+        _, kernel = csmc.get_independent_kernel(M0, G0, Mt, Gt, N, backward, Pt=Mt,
+                                                gradient=(kind == "independent-grad"), return_history=True)
+    state, hist = kernel(ExternalDraws([n_aux, normals], [u_res, u_bwd]), csmc.CSMCState(dev(x_star, dtype), None),
+                         dev(delta, dtype))
+    torch.cuda.synchronize()
+    compare(state, hist, want, dtype, C)
+
+
+def test_grad_log_target_matches_finite_differences():
+    from aux_ssm_samplers_b200 import csmc
+    rng = np.random.default_rng(3)
+    d, T = 3, 5
+    model = make_model(rng, d, T, "sv", torch.float64)
+    M0, G0, Mt, Gt = gpu_family(model, torch.float64)
+    u = rng.standard_normal((T, d))
+
+    def logp(u):
+        out = model.m0_logpdf(u[0]) + model.pot(0, u[0])
+        for t in range(1, T):
+            out += model.mt_logpdf(u[t], u[t - 1]) + model.pot(t, u[t])
+        return out
+
+    g = host(csmc.grad_log_target(dev(u[None], torch.float64), M0, G0, Mt, Gt))[0]
+    fd = np.zeros_like(u)
+    for idx in np.ndindex(*u.shape):
+        e = np.zeros_like(u)
+        e[idx] = 1e-6
+        fd[idx] = (logp(u + e) - logp(u - e)) / 2e-6
+    npt.assert_allclose(g, fd, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("backward", [True, False])
+def test_flat_potential_recovers_ar1_prior_on_gpu(backward):
+    # reference test_csmc.py:18-69 (N = 32, T = 5, rho = 0.9), run as 4096 independent chains x 60 sweeps
+    from aux_ssm_samplers_b200 import csmc
+    from aux_ssm_samplers_b200.draws import TorchDraws
+    rho, T, N, C = 0.9, 5, 32, 4096
+    f = lambda v: torch.tensor(v, dtype=torch.float32, device="cuda")
+    M0 = csmc.GaussianDistribution(f([0.0]), f([[1.0]]))
+    Mt = csmc.LinearGaussianDynamics(f([[rho]]), f([[1 - rho ** 2]]), f([0.0]))
+    G = csmc.FlatPotential()
+    init, kernel = csmc.get_kernel(M0, G, Mt, G, N, backward)
+    state = init(torch.zeros((C, T, 1), dtype=torch.float32, device="cuda"))
+    key = TorchDraws(1)
+    for _ in range(60):
+        state = kernel(key, state)
+    x = state.x[..., 0].double().cpu().numpy()
+    npt.assert_allclose(x.mean(0), 0.0, atol=0.05)
+    npt.assert_allclose(x.var(0), 1.0, atol=0.06)
+    npt.assert_allclose((x[:, 1:] * x[:, :-1]).mean(0), rho, atol=0.06)
+
+
+def test_api_errors_mirror_the_reference():
+    from aux_ssm_samplers_b200 import csmc
+    f = lambda v: torch.tensor(v, dtype=torch.float64, device="cuda")
+    M0 = csmc.GaussianDistribution(f([0.0]), f([[1.0]]))
+    Mt = csmc.LinearGaussianDynamics(f([[0.5]]), f([[0.75]]), f([0.0]))
+    G = csmc.FlatPotential()
+    with pytest.raises(ValueError):  # csmc/generic.py:44-45
+        csmc.get_generic_kernel(csmc.independent_factory(M0, G, Mt, G), 8, backward=True, Pt=None)
+    with pytest.raises(ValueError):  # csmc.py:49-50
+        csmc.get_kernel(M0, G, Mt, G, 8, backward=True, Pt=object())
+    with pytest.raises(NotImplementedError):
+        csmc.get_independent_kernel(M0, G, Mt, G, 8, parallel=True)
+    with pytest.raises(NotImplementedError):
+        csmc.get_kernel(object(), G, Mt, G, 8)
