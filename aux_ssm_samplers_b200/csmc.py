@@ -61,7 +61,7 @@ class GaussianDistribution(Distribution, UnivariatePotential):
 
     def __init__(self, m0, P0):
         self.m0, self.P0 = m0, P0
-        self.chol_P0 = torch.linalg.cholesky(P0) if P0.shape[-1] > 1 else torch.sqrt(P0)
+        self.chol_P0 = (torch.linalg.cholesky(P0) if P0.shape[-1] > 1 else torch.sqrt(P0)).contiguous()
 
     def logpdf(self, x):  # presence of this attribute is what the reference checks (csmc.py:49)
         raise NotImplementedError("evaluated inside the fused kernel")
@@ -73,7 +73,7 @@ class LinearGaussianDynamics(Dynamics):
 
     def __init__(self, F, Q, b):
         self.F, self.Q, self.b = F, Q, b
-        self.chol_Q = torch.linalg.cholesky(Q) if Q.shape[-1] > 1 else torch.sqrt(Q)
+        self.chol_Q = (torch.linalg.cholesky(Q) if Q.shape[-1] > 1 else torch.sqrt(Q)).contiguous()
 
     def logpdf(self, x_t_p_1, x_t, params):
         raise NotImplementedError("evaluated inside the fused kernel")
@@ -179,8 +179,10 @@ def _sweep(x_star, M0, Mt, pot, N, backward, resampling, key, aux=None, return_h
     else:
         nbytes = L.auxssm_csmc_scratch_bytes(desc, x.element_size())
         scratch = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
-    _lib.call("auxssm_csmc_sweep_" + sfx, _lib.stream_ptr(dev), desc, _lib.ptr(x), _lib.ptr(cvt(M0.m0)),
-              _lib.ptr(cvt(M0.chol_P0)), _lib.ptr(cvt(Mt.F)), _lib.ptr(cvt(Mt.b)), _lib.ptr(cvt(Mt.chol_Q)),
+    # converted copies must outlive the (asynchronous) call: keep them in locals, never pass temporaries
+    m0_, lp0_, f_, b_, lq_ = cvt(M0.m0), cvt(M0.chol_P0), cvt(Mt.F), cvt(Mt.b), cvt(Mt.chol_Q)
+    _lib.call("auxssm_csmc_sweep_" + sfx, _lib.stream_ptr(dev), desc, _lib.ptr(x), _lib.ptr(m0_),
+              _lib.ptr(lp0_), _lib.ptr(f_), _lib.ptr(b_), _lib.ptr(lq_),
               _lib.ptr(ys), _lib.ptr(u), _lib.ptr(shd), _lib.ptr(grad), _lib.ptr(K), _lib.ptr(cL),
               _lib.ptr(normals), _lib.ptr(u_res), _lib.ptr(u_kill), _lib.ptr(u_bwd), _lib.ptr(x_out), _lib.ptr(anc),
               _lib.ptr(xs_h), _lib.ptr(lw_h), _lib.ptr(a_h), _lib.ptr(scratch), int(nbytes))
@@ -312,8 +314,9 @@ def guided_gains(P0, Q, sqrt_half_delta):
     T, d = sqrt_half_delta.shape[0], P0.shape[-1]
     K = torch.empty((T, d, d), dtype=P0.dtype, device=dev)
     cL = torch.empty_like(K)
-    _lib.call("auxssm_guided_gains_" + sfx, _lib.stream_ptr(dev), T, d, _lib.ptr(P0.contiguous()),
-              _lib.ptr(Q.contiguous()), _lib.ptr(sqrt_half_delta.contiguous()), _lib.ptr(K), _lib.ptr(cL))
+    P0c, Qc, sc = P0.contiguous(), Q.contiguous(), sqrt_half_delta.contiguous()
+    _lib.call("auxssm_guided_gains_" + sfx, _lib.stream_ptr(dev), T, d, _lib.ptr(P0c), _lib.ptr(Qc), _lib.ptr(sc),
+              _lib.ptr(K), _lib.ptr(cL))
     return K, cL
 
 
