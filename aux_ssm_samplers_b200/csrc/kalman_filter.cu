@@ -301,6 +301,155 @@ __device__ __forceinline__ T run_recursion(const FilterArgs<T>& a, int c, int b,
   return ell;
 }
 
+// ---- fast recursion for H = I with DIAGONAL R_t -------------------------------------------------------
+// With independent scalar observations y_i = x_i + c_i + N(0, r_i) the measurement update of
+// filtering.py:84-130 factorises into d rank-one updates (sequential processing of observations):
+//     s = P_ii + r_i,  k = P[:, i] / s,  m += k (y_i - m_i - c_i),  P -= k k^T s,
+//     ell += log N(y_i; m_i + c_i, s)
+// which is algebraically the same posterior and the same joint log-likelihood (chain rule) without
+// any Cholesky factor or triangular solve: d^3 FMAs, no sqrt/divide chain.  Each thread keeps its
+// TM x TN tile of P in registers across the whole time loop; row i of the current P is exchanged
+// through a double-buffered shared vector (one barrier per scalar update).  Missing entries of y_t are
+// simply skipped.  When F is time-invariant and diagonal (AR(1)-type dynamics, e.g. the stochastic
+// volatility model) the predict step is done on the register tile as well: P <- f_a f_b P_ab + Q_ab.
+template <typename T, int D>
+__device__ __forceinline__ T run_recursion_scalar(const FilterArgs<T>& a, int c, int b, int t_begin, int t_end,
+                                                  StepBuf<T, D>& s) {
+  using Tl = Tile<D>;
+  constexpr int LD = Tl::LD, TM = Tl::TM, TN = Tl::TN, NT = Tl::NT, TX = D / TN, TILES = (D / TM) * TX;
+  const int d = a.d.dx;
+  const int tile = threadIdx.x;
+  const bool has = tile < TILES;
+  const int ty = has ? tile / TX : 0, tx = has ? tile % TX : 0;
+  T* rowbuf = s.W;          // 2 x (D + 4) words of the (otherwise unused) W buffer
+  T* svbuf = s.S;           // per-dimension innovation variance and squared innovation (S is unused here)
+  T* i2buf = s.S + D;
+  T p[TM][TN], mreg[TM];
+  T ell = T(0);
+  int parity = 0;
+
+  auto tile_load = [&]() {
+#pragma unroll
+    for (int r = 0; r < TM; ++r) {
+      if (has) ldv<T, TN>(p[r], s.P + (ty * TM + r) * LD + tx * TN);
+      mreg[r] = (has && tx == 0) ? s.m[ty * TM + r] : T(0);
+    }
+  };
+  auto tile_store = [&]() {
+#pragma unroll
+    for (int r = 0; r < TM; ++r) {
+      if (has) stv<T, TN>(s.P + (ty * TM + r) * LD + tx * TN, p[r]);
+      if (has && tx == 0) s.m[ty * TM + r] = mreg[r];
+    }
+  };
+  // all d scalar updates of one time step; returns the log-likelihood increment
+  auto scalar_updates = [&]() -> T {
+    for (int i0 = 0; i0 < d; i0 += TM) {
+#pragma unroll
+      for (int q = 0; q < TM; ++q) {
+        const int i = i0 + q;
+        if (i < d && !s.mask[i]) {  // uniform over the CTA
+          T* rb = rowbuf + parity * (D + 4);
+          parity ^= 1;
+          if (has && ty == i0 / TM) {
+            stv<T, TN>(rb + tx * TN, p[q]);
+            if (tx == 0) rb[D] = mreg[q];
+          }
+          cta_sync<D>();
+          const T sv = rb[i] + s.rd[i];
+          const T inv = T(1) / sv;
+          const T innov = s.y[i] - rb[D] - s.c[i];
+          if (has) {
+            T ra[TM], rc[TN];
+            ldv<T, TM>(ra, rb + ty * TM);
+            ldv<T, TN>(rc, rb + tx * TN);
+#pragma unroll
+            for (int r = 0; r < TM; ++r) {
+              const T kr = ra[r] * inv;
+#pragma unroll
+              for (int cc = 0; cc < TN; ++cc) p[r][cc] = fma_(-kr, rc[cc], p[r][cc]);
+              if (tx == 0) mreg[r] = fma_(kr, innov, mreg[r]);
+            }
+          }
+          if (threadIdx.x == 0) { svbuf[i] = sv; i2buf[i] = innov * innov * inv; }
+        }
+      }
+    }
+    cta_sync<D>();
+    T part = T(0);
+    const int i = threadIdx.x;
+    if (i < d && !s.mask[i]) part = T(-0.5) * i2buf[i] - T(0.5) * log(svbuf[i]) - half_log_2pi<T>();
+    T e = cta_sum<T, D>(part, s.red);
+    if (!(e == e)) e = T(0);
+    return e;
+  };
+
+  // is F time-invariant and diagonal?  (decided once per CTA)
+  bool fdiag = false;
+  int t = t_begin;
+  bool first_dyn = true, first_obs = true;
+  if (t == 0) {
+    cta_sync<D>();
+    if (threadIdx.x < d) s.m[threadIdx.x] = a.m0[unit_off(a.d.m0, c, b) + threadIdx.x];
+    load_mat<T, D, false>(a.P0 + unit_off(a.d.P0, c, b), s.P, d, d);
+    const int n_obs = stage_obs<T, D>(a, c, b, 0, true, s, nullptr, false);
+    first_obs = false;
+    tile_load();
+    if (n_obs > 0) ell += scalar_updates();
+    tile_store();
+    store_state<T, D>(a, c, b, 0, s);
+    t = 1;
+  } else {
+    cta_sync<D>();
+    tile_load();
+  }
+  for (; t < t_end; ++t) {
+    stage_dyn<T, D>(a, c, b, t - 1, first_dyn, s.Ft, nullptr, s.Q, s.bv);
+    if (first_dyn) {
+      int off = 0;
+      if (a.d.Fs.time == 0) {
+        AUXSSM_FOR_ROWS(ri, rj, d, d) if (ri != rj && s.Ft[ri * LD + rj] != T(0)) off = 1;
+      } else {
+        off = 1;
+      }
+      fdiag = (Tl::NT == 32) ? (__any_sync(0xffffffffu, off) == 0) : (__syncthreads_or(off) == 0);
+    }
+    first_dyn = false;
+    const int n_obs = stage_obs<T, D>(a, c, b, t, first_obs, s, nullptr, false);
+    first_obs = false;
+    if (fdiag) {
+      // predict on the register tile: P_ab <- f_a f_b P_ab + Q_ab ; m_a <- f_a m_a + b_a
+#pragma unroll
+      for (int r = 0; r < TM; ++r) {
+        if (has) {
+          const int ra = ty * TM + r;
+          const T fa = s.Ft[ra * LD + ra];
+          T qv[TN];
+          ldv<T, TN>(qv, s.Q + ra * LD + tx * TN);
+#pragma unroll
+          for (int cc = 0; cc < TN; ++cc) {
+            const int cb = tx * TN + cc;
+            p[r][cc] = fma_(fa * s.Ft[cb * LD + cb], p[r][cc], qv[cc]);
+          }
+          if (tx == 0) mreg[r] = fma_(fa, mreg[r], s.bv[ra]);
+        }
+      }
+    } else {
+      tile_store();
+      kalman_predict<T, D>(s, d);   // dense F: two products in shared memory (uses W)
+      symmetrize<T, D>(s.P, d);
+      tile_load();
+      cta_sync<D>();
+    }
+    if (n_obs > 0) ell += scalar_updates();
+    cta_sync<D>();
+    tile_store();
+    store_state<T, D>(a, c, b, t, s);
+  }
+  cta_sync<D>();
+  return ell;
+}
+
 __device__ __forceinline__ void chunk_range(int j, int chunk_len, int T, int& t0, int& t1) {
   // chunk j covers scan elements t in [1 + j*len, 1 + (j+1)*len) ; chunk 0 additionally owns t = 0
   t0 = (j == 0) ? 0 : 1 + j * chunk_len;
@@ -330,7 +479,8 @@ __global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) filter_recursion
     if (threadIdx.x < dx) s.m[threadIdx.x] = pf[threadIdx.x];
     load_mat<T, D, false>(pf + dx, s.P, dx, dx);
   }
-  const T ell = run_recursion<T, D, HID>(a, c, b, t0, t1, s);
+  const bool scalar_path = HID && (a.d.flags & AUXSSM_FLAG_R_DIAGONAL) != 0;
+  const T ell = scalar_path ? run_recursion_scalar<T, D>(a, c, b, t0, t1, s) : run_recursion<T, D, HID>(a, c, b, t0, t1, s);
   cta_sync<D>();
   if (j + 1 < a.n_chunks && j == 0) {
     T* pf = a.prefix + ((int64_t)unit * a.n_chunks + j) * psz;

@@ -131,16 +131,35 @@ __global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) sample_recursion
   last_step<T, D>(s, dx);
   store_x<T, D>(a, c, b, Tn - 1, s.x);
   bool first = true;
+  int fdiag_known = 0;
   for (int t = Tn - 2; t >= t0; --t) {
     load_step_inputs<T, D>(a, c, b, t, first, s, true);
     first = false;
-    // factorisations
-    mm_tn<T, D, 0>(s.P, s.Ft, s.W, nullptr, dx);   // W = P F^T
-    mm_tn<T, D, 1>(s.Ft, s.W, s.S, s.Q, dx);       // S = F P F^T + Q
-    symmetrize<T, D>(s.S, dx);
-    mm_tn<T, D, 0>(s.Ft, s.P, s.Z, nullptr, dx);   // Z = F P
-    mv_tn<T, D, 1>(s.Ft, s.m, s.r, s.bv, dx, dx);  // r = F m + b
-    if (threadIdx.x < dx) s.r[threadIdx.x] = s.x[threadIdx.x] - s.r[threadIdx.x];  // x_{t+1} - F m - b
+    if (fdiag_known == 0) {  // is F time-invariant and diagonal?  (decided once per CTA)
+      int off = (a.d.Fs.time != 0) ? 1 : 0;
+      AUXSSM_FOR_ROWS(ri, rj, dx, dx) if (ri != rj && s.Ft[ri * LD + rj] != T(0)) off = 1;
+      fdiag_known = (__syncthreads_or(off) == 0) ? 1 : -1;
+    }
+    if (fdiag_known > 0) {
+      // diagonal F: S_ab = f_a f_b P_ab + Q_ab, (F P)_ab = f_a P_ab, r = x_{t+1} - f m - b  (O(d^2))
+      AUXSSM_FOR_ROWS(ri, rj, dx, dx) {
+        const T fa = s.Ft[ri * LD + ri], pv = s.P[ri * LD + rj];
+        s.S[ri * LD + rj] = fma_(fa * s.Ft[rj * LD + rj], pv, s.Q[ri * LD + rj]);
+        s.Z[ri * LD + rj] = fa * pv;
+      }
+      if (threadIdx.x < dx) {
+        const int ri = threadIdx.x;
+        s.r[ri] = s.x[ri] - fma_(s.Ft[ri * LD + ri], s.m[ri], s.bv[ri]);
+      }
+      cta_sync<D>();
+    } else {
+      mm_tn<T, D, 0>(s.P, s.Ft, s.W, nullptr, dx);   // W = P F^T
+      mm_tn<T, D, 1>(s.Ft, s.W, s.S, s.Q, dx);       // S = F P F^T + Q
+      symmetrize<T, D>(s.S, dx);
+      mm_tn<T, D, 0>(s.Ft, s.P, s.Z, nullptr, dx);   // Z = F P
+      mv_tn<T, D, 1>(s.Ft, s.m, s.r, s.bv, dx, dx);  // r = F m + b
+      if (threadIdx.x < dx) s.r[threadIdx.x] = s.x[threadIdx.x] - s.r[threadIdx.x];  // x_{t+1} - F m - b
+    }
     chol_inplace<T, D>(s.S, s.dg, dx);
     fwd_solve<T, D>(s.S, s.Z, s.r, dx, dx, s.dg);        // Zs = Ls^{-1} F P ; r <- Ls^{-1} r
     mm_tn<T, D, 2>(s.Z, s.Z, s.P, s.P, dx);        // Sigma = P - Zs^T Zs

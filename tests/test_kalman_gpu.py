@@ -216,7 +216,8 @@ def test_sv_sweep_vs_oracle(dtype, order, seed, parallel, dense_R):
 @pytest.mark.parametrize("d,T,C", [(3, 11, 2), (30, 40, 3), (64, 9, 2)])
 @pytest.mark.parametrize("dense_h", [False, True])
 @pytest.mark.parametrize("chunks", [1, 3])
-def test_filter_and_logpdf_diagonal_R(dtype, d, T, C, dense_h, chunks):
+@pytest.mark.parametrize("fkind", ["dense", "diag", "diag-shared"])
+def test_filter_and_logpdf_diagonal_R(dtype, d, T, C, dense_h, chunks, fkind):
     """AUXSSM_FLAG_R_DIAGONAL: diag(R_t) passed as [C, T, d] must equal the dense-R oracle."""
     from aux_ssm_samplers_b200 import kalman
     if d == 64 and dtype == torch.float64 and (dense_h or chunks > 1):
@@ -226,6 +227,10 @@ def test_filter_and_logpdf_diagonal_R(dtype, d, T, C, dense_h, chunks):
     lg = list(lg)
     rdiag = rng.uniform(0.05, 1.0, size=(C, T, d))
     lg[6] = rdiag[..., :, None] * np.eye(d)
+    if fkind == "diag":          # time-varying diagonal F: dense predict path
+        lg[2] = rng.uniform(0.5, 0.95, size=(C, T - 1, d))[..., :, None] * np.eye(d)
+    elif fkind == "diag-shared":  # time-invariant diagonal F: O(d^2) predict on the register tile
+        lg[2] = np.broadcast_to(np.diag(rng.uniform(0.5, 0.95, size=d)), (C, T - 1, d, d)).copy()
     if not dense_h:
         lg[5] = np.broadcast_to(np.eye(d), (C, T, d, d)).copy()
         lg[7] = np.zeros((C, T, d))
@@ -234,6 +239,8 @@ def test_filter_and_logpdf_diagonal_R(dtype, d, T, C, dense_h, chunks):
     ems, ePs, eell = ok.filtering(ys, lg, False)
     glg = [dev(a, dtype) for a in lg]
     glg[6] = kalman.Diagonal(dev(rdiag, dtype))
+    if fkind == "diag-shared":
+        glg[2] = dev(lg[2][:1, :1], dtype)  # [1, 1, d, d]: stride 0 over chains and time
     if not dense_h:
         glg[5] = glg[7] = None
     ms, Ps, ell = kalman.filtering(dev(ys, dtype), glg, chunks > 1, time_chunks=chunks)
@@ -270,3 +277,22 @@ def test_logpdf_fast_path_time_invariant(dtype, d, T, C):
                         ok.log_likelihood(ys, xs, full), rtol=r)
     npt.assert_allclose(host(kalman.posterior_logpdf(dev(ys, dtype), dev(xs, dtype), dev(ell, dtype), glg)),
                         ok.posterior_logpdf(ys, xs, ell, full), rtol=r)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("d,T,C", [(3, 9, 2), (30, 33, 3)])
+def test_sampling_time_invariant_diagonal_F(dtype, d, T, C):
+    from aux_ssm_samplers_b200 import kalman
+    rng = np.random.default_rng(d)
+    ys, lg = random_lgssm(rng, T, d, d, lead=(C,), stable=True)
+    lg = list(lg)
+    F = np.diag(rng.uniform(0.5, 0.95, size=d))
+    lg[2] = np.broadcast_to(F, (C, T - 1, d, d)).copy()
+    ms, Ps, _ = ok.filtering(ys, lg, False)
+    eps = rng.standard_normal((C, T, d))
+    exs = ok.sampling(eps, ms, Ps, lg, False)
+    glg = [dev(a, dtype) for a in lg]
+    glg[2] = dev(F[None], dtype)
+    xs = kalman.sampling(dev(eps, dtype), dev(ms, dtype), dev(Ps, dtype), glg, False)
+    r = TOL[dtype]["rtol"]
+    npt.assert_allclose(host(xs), exs, rtol=r, atol=r * max(1.0, np.abs(exs).max()) * (10 if dtype == torch.float32 else 1))
