@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libauxssm.so")
 AUXSSM_MAX_DIM = 64
 FLAG_H_IDENTITY = 1
 FLAG_R_DIAGONAL = 2
+FLAG_F_IS_DIAGONAL = 4
 LOGPDF_PRIOR, LOGPDF_LOGLIK, LOGPDF_MINUS_ELL, LOGPDF_POSTERIOR = 1, 2, 4, 7
 
 

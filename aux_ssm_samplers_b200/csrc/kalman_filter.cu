@@ -490,6 +490,171 @@ __global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) filter_recursion
   if (threadIdx.x == 0) a.ellpart[(int64_t)unit * a.n_chunks + j] = ell;
 }
 
+// ---- one warp per chain: H = I, diagonal R_t, time-invariant diagonal F, Q, b ---------------------------
+// The structured case of every auxiliary Kalman sampler whose latent dynamics are AR(1)-type (e.g. the
+// stochastic-volatility model).  The whole recursion lives in the registers of ONE warp: lane (ty, tx) of
+// a 4 x 8 lane grid owns a (D/4) x (D/8) tile of P, of Q and of f f^T; the predict step is 1 FMA per
+// element, the measurement update is d rank-one updates (see run_recursion_scalar) with row i exchanged
+// through a double-buffered shared vector and __syncwarp only (no block barrier anywhere).  y_{t+1} and
+// diag(R_{t+1}) are prefetched into registers one step ahead so DRAM latency never sits on the critical
+// path; P_t / m_t are staged through shared memory and written with row-contiguous (coalesced) stores.
+template <typename T, int D>
+__global__ void __launch_bounds__(128, 2)
+filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
+  // Four chains per CTA, one per warp: warps are bound to the four SM sub-partitions by their index
+  // inside the CTA, so single-warp CTAs would all queue on one scheduler.
+  constexpr int GY = 4, GX = 8, TM = D / GY, TN = D / GX, LDS_ = D + 4, WPC = 4;
+  __shared__ __align__(16) T stage_[WPC][D * LDS_];
+  __shared__ __align__(16) T rowbuf_[WPC][2 * (D + 4)];
+  __shared__ T ev_[WPC][D], rdv_[WPC][D], svbuf_[WPC][D], mvec_[WPC][D];
+  const int wq = threadIdx.x >> 5;
+  T* stage = stage_[wq];
+  T* rowbuf = rowbuf_[wq];
+  T *ev = ev_[wq], *rdv = rdv_[wq], *svbuf = svbuf_[wq], *mvec = mvec_[wq];
+  const int lane = threadIdx.x & 31, ty = lane / GX, tx = lane % GX;
+  const int j = chunk_first + blockIdx.y, unit = blockIdx.x * WPC + wq;
+  if (unit >= a.d.n_chains * a.d.n_batch) return;  // whole warp; only __syncwarp is used below
+  const int c = unit / a.d.n_batch, b = unit % a.d.n_batch;
+  const int d = a.d.dx, Tn = a.d.T;
+  int t0, t1;
+  chunk_range(j, a.chunk_len, Tn, t0, t1);
+
+  // time-invariant parameters -> registers
+  const T* Fg = a.Fs ? a.Fs + unit_off(a.d.Fs, c, b) : nullptr;
+  const T* Qg = a.Qs ? a.Qs + unit_off(a.d.Qs, c, b) : nullptr;
+  const T* bg = a.bs ? a.bs + unit_off(a.d.bs, c, b) : nullptr;
+  T p[TM][TN], q[TM][TN], mreg[TM], fa[TM], fc[TN], ba[TM];
+#pragma unroll
+  for (int cc = 0; cc < TN; ++cc) {
+    const int cb = tx * TN + cc;
+    fc[cc] = (Fg && cb < d) ? Fg[cb * d + cb] : T(0);
+  }
+#pragma unroll
+  for (int r = 0; r < TM; ++r) {
+    const int ra = ty * TM + r;
+    fa[r] = (Fg && ra < d) ? Fg[ra * d + ra] : T(0);
+    ba[r] = (bg && ra < d) ? bg[ra] : T(0);
+#pragma unroll
+    for (int cc = 0; cc < TN; ++cc) {
+      const int cb = tx * TN + cc;
+      const bool in = ra < d && cb < d;
+      q[r][cc] = (Qg && in) ? Qg[ra * d + cb] : T(0);
+    }
+  }
+  // initial state: prior (chunk 0) or the incoming prefix
+  const int psz = d + d * d;
+  const T* m_src = (j == 0) ? a.m0 + unit_off(a.d.m0, c, b) : a.prefix + ((int64_t)unit * a.n_chunks + (j - 1)) * psz;
+  const T* P_src = (j == 0) ? a.P0 + unit_off(a.d.P0, c, b) : m_src + d;
+#pragma unroll
+  for (int r = 0; r < TM; ++r) {
+    const int ra = ty * TM + r;
+    mreg[r] = (tx == 0 && ra < d) ? m_src[ra] : T(0);
+#pragma unroll
+    for (int cc = 0; cc < TN; ++cc) {
+      const int cb = tx * TN + cc;
+      p[r][cc] = (ra < d && cb < d) ? P_src[ra * d + cb] : T(0);
+    }
+  }
+  const T* yg = a.ys + unit_off(a.d.ys, c, b);
+  const T* rg = a.Rs + unit_off(a.d.Rs, c, b);
+  const T* cg = a.cs ? a.cs + unit_off(a.d.cs, c, b) : nullptr;
+  T* msg = a.ms + unit_off(a.d.ms, c, b);
+  T* Psg = a.Ps + unit_off(a.d.Ps, c, b);
+  // prefetch the first step's observation
+  T y_n = T(0), r_n = T(1), c_n = T(0);
+  if (lane < d) {
+    y_n = yg[(int64_t)t0 * a.d.ys.time + lane];
+    r_n = rg[(int64_t)t0 * a.d.Rs.time + lane];
+    if (cg) c_n = cg[(int64_t)t0 * a.d.cs.time + lane];
+  }
+  if (D > 32) { /* lanes cover at most 32 dimensions: this kernel is instantiated for D <= 32 only */ }
+  T ell = T(0);
+  int parity = 0;
+  for (int t = t0; t < t1; ++t) {
+    // ---- observation of this step -> shared; prefetch the next one ----
+    const T y_c = y_n, r_c = r_n, c_c = c_n;
+    if (t + 1 < t1 && lane < d) {
+      y_n = yg[(int64_t)(t + 1) * a.d.ys.time + lane];
+      r_n = rg[(int64_t)(t + 1) * a.d.Rs.time + lane];
+      if (cg) c_n = cg[(int64_t)(t + 1) * a.d.cs.time + lane];
+    }
+    const bool obs = (lane < d) && finite_(y_c);
+    const unsigned obs_mask = __ballot_sync(0xffffffffu, obs);
+    if (lane < D) { ev[lane] = y_c - c_c; rdv[lane] = r_c; }
+    // ---- predict (not for the very first time step of the model) ----
+    if (t > 0) {
+#pragma unroll
+      for (int r = 0; r < TM; ++r) {
+#pragma unroll
+        for (int cc = 0; cc < TN; ++cc) p[r][cc] = fma_(fa[r] * fc[cc], p[r][cc], q[r][cc]);
+        mreg[r] = fma_(fa[r], mreg[r], ba[r]);
+      }
+    }
+    __syncwarp();
+    // ---- d scalar measurement updates ----
+    T quad = T(0);
+#pragma unroll
+    for (int i0 = 0; i0 < D; i0 += TM) {
+#pragma unroll
+      for (int qq = 0; qq < TM; ++qq) {
+        const int i = i0 + qq;
+        if (i < d && ((obs_mask >> i) & 1u)) {  // warp-uniform
+          T* rb = rowbuf + parity * (D + 4);
+          parity ^= 1;
+          if (ty == i0 / TM) {
+            stv<T, TN>(rb + tx * TN, p[qq]);
+            if (tx == 0) rb[D] = mreg[qq];
+          }
+          __syncwarp();
+          const T sv = rb[i] + rdv[i];
+          const T inv = T(1) / sv;
+          const T innov = ev[i] - rb[D];
+          T ra[TM], rc[TN];
+          ldv<T, TM>(ra, rb + ty * TM);
+          ldv<T, TN>(rc, rb + tx * TN);
+#pragma unroll
+          for (int r = 0; r < TM; ++r) {
+            const T kr = ra[r] * inv;
+#pragma unroll
+            for (int cc = 0; cc < TN; ++cc) p[r][cc] = fma_(-kr, rc[cc], p[r][cc]);
+            mreg[r] = fma_(kr, innov, mreg[r]);  // only the tx == 0 copies are ever read
+          }
+          quad = fma_(innov * innov, inv, quad);
+          if (lane == 0) svbuf[i] = sv;
+        }
+      }
+    }
+    // ---- log-likelihood increment of this step (nan_to_num -> 0, filtering.py:125) ----
+    __syncwarp();
+    T part = ((lane < d) && ((obs_mask >> lane) & 1u)) ? T(-0.5) * log(svbuf[lane]) - half_log_2pi<T>() : T(0);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    T inc = part - T(0.5) * quad;
+    if (!(inc == inc)) inc = T(0);
+    if (obs_mask != 0u) ell += inc;
+    // ---- outputs: tile -> shared -> coalesced rows ----
+#pragma unroll
+    for (int r = 0; r < TM; ++r) {
+      stv<T, TN>(stage + (ty * TM + r) * LDS_ + tx * TN, p[r]);
+      if (tx == 0) mvec[ty * TM + r] = mreg[r];
+    }
+    __syncwarp();
+    T* Pt = Psg + (int64_t)t * a.d.Ps.time;
+    for (int r = 0; r < d; ++r)
+      if (lane < d) Pt[r * d + lane] = stage[r * LDS_ + lane];
+    if (lane < d) msg[(int64_t)t * a.d.ms.time + lane] = mvec[lane];
+    __syncwarp();
+  }
+  // chunk outputs
+  if (j == 0 && j + 1 < a.n_chunks) {
+    T* pf = a.prefix + ((int64_t)unit * a.n_chunks + j) * psz;
+    if (lane < d) pf[lane] = mvec[lane];
+    for (int r = 0; r < d; ++r)
+      if (lane < d) pf[d + r * d + lane] = stage[r * LDS_ + lane];
+  }
+  if (lane == 0) a.ellpart[(int64_t)unit * a.n_chunks + j] = ell;
+}
+
 // ---- parallel-in-time: elements and the associative combine ------------------------------------
 
 template <typename T, int D> struct ScanBuf {
@@ -725,8 +890,17 @@ static int launch_filter(cudaStream_t st, const FilterArgs<T>& a) {
   auto rec = hid ? filter_recursion_kernel<T, D, true> : filter_recursion_kernel<T, D, false>;
   int rc = ensure_smem(rec, smem_step, "auxssm_kalman_filter");
   if (rc) return rc;
-  rec<<<dim3(units, 1), NT, smem_step, st>>>(a, 0);
-  AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (recursion, chunk 0)");
+  // structured fast path: H = I, diagonal R, time-invariant diagonal F / Q / b -> one warp per chain
+  const uint32_t need = AUXSSM_FLAG_H_IDENTITY | AUXSSM_FLAG_R_DIAGONAL | AUXSSM_FLAG_F_IS_DIAGONAL;
+  const bool warp_path = D >= 8 && D <= 32 && (a.d.flags & need) == need &&
+                         (a.d.T == 1 || (a.d.Fs.time == 0 && a.d.Qs.time == 0 && a.d.bs.time == 0));
+  if (warp_path) {
+    filter_warp_kernel<T, (D >= 8 && D <= 32) ? D : 8><<<dim3((units + 3) / 4, 1), 128, 0, st>>>(a, 0);
+    AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (warp recursion, chunk 0)");
+  } else {
+    rec<<<dim3(units, 1), NT, smem_step, st>>>(a, 0);
+    AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (recursion, chunk 0)");
+  }
   if (a.n_chunks > 1) {
     const size_t smem_scan = scan_smem_elems<D>() * sizeof(T);
     if (a.n_chunks > 2) {
@@ -739,8 +913,13 @@ static int launch_filter(cudaStream_t st, const FilterArgs<T>& a) {
       filter_prefix_kernel<T, D><<<units, NT, smem_scan, st>>>(a);
       AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (prefix)");
     }
-    rec<<<dim3(units, a.n_chunks - 1), NT, smem_step, st>>>(a, 1);
-    AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (recursion, chunks >= 1)");
+    if (warp_path) {
+      filter_warp_kernel<T, (D >= 8 && D <= 32) ? D : 8><<<dim3((units + 3) / 4, a.n_chunks - 1), 128, 0, st>>>(a, 1);
+      AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (warp recursion, chunks >= 1)");
+    } else {
+      rec<<<dim3(units, a.n_chunks - 1), NT, smem_step, st>>>(a, 1);
+      AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (recursion, chunks >= 1)");
+    }
   }
   return AUXSSM_OK;
 }

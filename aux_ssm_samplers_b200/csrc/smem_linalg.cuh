@@ -21,7 +21,9 @@ template <int D> struct Tile;
 template <> struct Tile<4>  { static constexpr int LD = 4,  NT = 32,  TM = 1, TN = 1; };
 template <> struct Tile<8>  { static constexpr int LD = 12, NT = 32,  TM = 1, TN = 2; };
 template <> struct Tile<16> { static constexpr int LD = 20, NT = 32,  TM = 2, TN = 4; };
-template <> struct Tile<32> { static constexpr int LD = 36, NT = 64,  TM = 4, TN = 4; };
+// D = 32 runs as ONE warp per work item (8 x 4 register tiles, __syncwarp only): with two warps one of them
+// idled at a block barrier during every Cholesky / triangular-solve phase.
+template <> struct Tile<32> { static constexpr int LD = 36, NT = 32,  TM = 8, TN = 4; };
 template <> struct Tile<64> { static constexpr int LD = 68, NT = 256, TM = 4, TN = 4; };
 
 // Resident CTAs per SM the kernels are compiled for: caps registers at 128/thread for D <= 32 so that
@@ -311,6 +313,17 @@ __device__ __forceinline__ void fwd_solve_reg(const T* L, T* B, T* bvec, const T
   constexpr int V = (D >= 4) ? 4 : D;
   cta_sync<D>();
   const int j = threadIdx.x;
+  if (bvec != nullptr && m >= Tile<D>::NT) {
+    // no spare thread for the extra right-hand side: thread 0 solves it first (m == NT == D only)
+    if (j == 0) {
+      for (int i = 0; i < n; ++i) {
+        T acc = bvec[i];
+        for (int k = 0; k < i; ++k) acc = fma_(-L[i * LD + k], bvec[k], acc);
+        bvec[i] = acc * dginv[i];
+      }
+    }
+    cta_sync<D>();
+  }
   const bool is_vec = (j == m) && (bvec != nullptr);
   if (j < m || is_vec) {
     T z[D];

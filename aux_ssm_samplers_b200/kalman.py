@@ -124,13 +124,14 @@ def _infer_dims(ys, m0, inner_batch, xs=None):
     return _Dims(C, B, T, dx, dy, has_chain, inner_batch)
 
 
-def _fill_desc(dims, parallel, time_chunks, hid, rdiag=False):
+def _fill_desc(dims, parallel, time_chunks, hid, rdiag=False, fdiag=False):
     d = LgssmDesc()
     d.T, d.dx, d.dy = dims.T, dims.dx, dims.dy
     d.n_chains, d.n_batch = dims.C, dims.B
     d.parallel = 1 if parallel else 0
     d.time_chunks = int(time_chunks)
-    d.flags = (_lib.FLAG_H_IDENTITY if hid else 0) | (_lib.FLAG_R_DIAGONAL if rdiag else 0)
+    d.flags = ((_lib.FLAG_H_IDENTITY if hid else 0) | (_lib.FLAG_R_DIAGONAL if rdiag else 0)
+               | (_lib.FLAG_F_IS_DIAGONAL if fdiag else 0))
     return d
 
 
@@ -182,11 +183,14 @@ def _prep_lgssm(d, dims, lgssm, dtype):
 # primitives
 # --------------------------------------------------------------------------------------------
 
-def filtering(ys, lgssm, parallel, *, inner_batch=False, time_chunks=0):
+def filtering(ys, lgssm, parallel, *, inner_batch=False, time_chunks=0, f_diagonal=False):
     """Kalman filter; returns ``(ms, Ps, ell)`` like the reference (filtering.py:18-46).
 
     ``ell`` is summed over the inner batch (filtering.py:43-45) and has shape ``[C]`` (or ``[]``).
     ``time_chunks`` (parallel only) forces the number of time chunks of the scan; 0 = automatic.
+    ``f_diagonal=True`` is a promise that every ``F_t`` is a diagonal matrix (layout unchanged); together
+    with ``Hs=None``, ``Rs=Diagonal(...)`` and time-invariant ``Fs, Qs, bs`` it selects the one-warp-per-chain
+    structured kernel.
     """
     lgssm = LGSSM(*lgssm)
     dev = _lib.require_cuda(ys, *_tensors(lgssm))
@@ -194,7 +198,7 @@ def filtering(ys, lgssm, parallel, *, inner_batch=False, time_chunks=0):
     sfx = _lib.suffix(dtype)
     dims = _infer_dims(ys, lgssm.m0, inner_batch)
     hid = lgssm.Hs is None
-    d = _fill_desc(dims, parallel, time_chunks, hid, isinstance(lgssm.Rs, Diagonal))
+    d = _fill_desc(dims, parallel, time_chunks, hid, isinstance(lgssm.Rs, Diagonal), f_diagonal)
     p = _prep_lgssm(d, dims, lgssm, dtype)
     ysc, d.ys = _canon(ys, (dims.dy,), dims.T, dims, "ys")
     ms = torch.empty(_out_shape(dims, dims.T, (dims.dx,)), dtype=dtype, device=dev)
@@ -212,7 +216,7 @@ def filtering(ys, lgssm, parallel, *, inner_batch=False, time_chunks=0):
     return ms, Ps, (ell if dims.has_chain else ell[0])
 
 
-def sampling(key, ms, Ps, lgssm, parallel, *, inner_batch=False, time_chunks=0):
+def sampling(key, ms, Ps, lgssm, parallel, *, inner_batch=False, time_chunks=0, f_diagonal=False):
     """Backward sampler (sampling.py:11-40).  ``key`` supplies ``normal(ms.shape)`` (sampling.py:128);
     a plain tensor of that shape is accepted as the draws themselves."""
     lgssm = LGSSM(*lgssm)
@@ -224,7 +228,7 @@ def sampling(key, ms, Ps, lgssm, parallel, *, inner_batch=False, time_chunks=0):
         raise AuxssmError("eps must have the shape of ms, got %s vs %s" % (tuple(eps.shape), tuple(ms.shape)))
     dims = _infer_dims(None, lgssm.m0, inner_batch, xs=ms)
     dims = dims._replace(dx=ms.shape[-1], dy=ms.shape[-1])
-    d = _fill_desc(dims, parallel, time_chunks, True)
+    d = _fill_desc(dims, parallel, time_chunks, True, False, f_diagonal)
     dx, Tm1 = dims.dx, dims.T - 1
     msc, d.ms = _canon(ms, (dx,), dims.T, dims, "ms")
     Psc, d.Ps = _canon(Ps, (dx, dx), dims.T, dims, "Ps")
@@ -335,7 +339,8 @@ def mh_accept(x, x_prop, u, delta, log_lgssm_prop, log_lgssm_rev, log_target_pro
 # kernel constructor
 # --------------------------------------------------------------------------------------------
 
-def get_kernel(dynamics_factory, observations_factory, log_likelihood_fn, parallel, *, time_chunks=0):
+def get_kernel(dynamics_factory, observations_factory, log_likelihood_fn, parallel, *, time_chunks=0,
+               f_diagonal=False):
     """Auxiliary Kalman sampler: returns ``(init, kernel)`` exactly like the reference
     (kalman/generic.py:19-95; note the reference's docstring lists them the other way round).
 
@@ -348,9 +353,10 @@ def get_kernel(dynamics_factory, observations_factory, log_likelihood_fn, parall
         m0, P0, Fs, Qs, bs, *_ = dynamics_factory(x)
         ys, Hs, Rs, cs, *_ = observations_factory(x, u, delta)
         lgssm = LGSSM(m0, P0, Fs, Qs, bs, Hs, Rs, cs)
-        ms, Ps, ell = filtering(ys, lgssm, parallel, time_chunks=time_chunks)
+        ms, Ps, ell = filtering(ys, lgssm, parallel, time_chunks=time_chunks, f_diagonal=f_diagonal)
         if x_prop is None:
-            x_prop = sampling(sampling_key, ms, Ps, lgssm, parallel, time_chunks=time_chunks)
+            x_prop = sampling(sampling_key, ms, Ps, lgssm, parallel, time_chunks=time_chunks,
+                              f_diagonal=f_diagonal)
         log_lgssm = posterior_logpdf(ys, x_prop, ell, lgssm)
         return log_lgssm, log_likelihood_fn(x_prop), x_prop
 

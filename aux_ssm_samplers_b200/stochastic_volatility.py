@@ -68,6 +68,9 @@ def log_potential(ys, x, out=None):
 def get_kernel(ys, m0, P0, F, Q, b, parallel, order=1, *, time_chunks=0, dense_R=False):
     """auxiliary_kalman.py:10-57: auxiliary Kalman sampler for the SV model, first or second order."""
     d = m0.shape[0]
+    # one-off structural check at construction time (not on the sweep path): diagonal F selects the
+    # structured one-warp-per-chain filter kernel
+    f_diagonal = bool((F - torch.diag(torch.diagonal(F))).abs().max().item() == 0.0)
     Fs, Qs, bs = F.reshape(1, d, d), Q.reshape(1, d, d), b.reshape(1, d)  # time-invariant: stride 0, never tiled
 
     def dynamics_factory(_x):
@@ -82,4 +85,5 @@ def get_kernel(ys, m0, P0, F, Q, b, parallel, order=1, *, time_chunks=0, dense_R
         out = kalman.prior_logpdf(x, prior_lgssm)  # mvn.logpdf(x0; m0, P0) + sum_t mvn.logpdf(x_t; F x_{t-1} + b, Q)
         return log_potential(ys, x, out=out)
 
-    return kalman.get_kernel(dynamics_factory, obs_factory, log_likelihood_fn, parallel, time_chunks=time_chunks)
+    return kalman.get_kernel(dynamics_factory, obs_factory, log_likelihood_fn, parallel, time_chunks=time_chunks,
+                             f_diagonal=f_diagonal)

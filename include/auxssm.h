@@ -54,6 +54,7 @@ typedef struct auxssm_stride {
 /* flags */
 #define AUXSSM_FLAG_H_IDENTITY 1u /* Hs == NULL: H_t = I (requires dy == dx), c_t = 0 if cs == NULL */
 #define AUXSSM_FLAG_R_DIAGONAL 2u /* Rs holds diag(R_t): core shape [dy] instead of [dy, dy]          */
+#define AUXSSM_FLAG_F_IS_DIAGONAL 4u /* hint: every F_t is a diagonal matrix (layout unchanged, [dx, dx]) */
 
 /*
  * Linear-Gaussian state-space model, mirrors the LGSSM NamedTuple

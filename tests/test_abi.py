@@ -42,7 +42,7 @@ def test_descriptor_validation_without_gpu(lib):
     assert lib.auxssm_kalman_filter_scratch_bytes(d, 8) > 0
     assert lib.auxssm_kalman_sample_scratch_bytes(d, 8) > 0
     d.parallel = 0
-    assert lib.auxssm_kalman_sample_scratch_bytes(d, 8) == 0
+    assert lib.auxssm_kalman_sample_scratch_bytes(d, 8) >= 8 * (3 * 3 + 3) * 8  # (G_t, e_t) elements
     # null data pointers are rejected before any launch
     rc = lib.auxssm_kalman_filter_f64(None, d, *([None] * 12), None, 0)
     assert rc == -1 and b"null" in lib.auxssm_last_error()

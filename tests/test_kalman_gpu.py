@@ -243,7 +243,8 @@ def test_filter_and_logpdf_diagonal_R(dtype, d, T, C, dense_h, chunks, fkind):
         glg[2] = dev(lg[2][:1, :1], dtype)  # [1, 1, d, d]: stride 0 over chains and time
     if not dense_h:
         glg[5] = glg[7] = None
-    ms, Ps, ell = kalman.filtering(dev(ys, dtype), glg, chunks > 1, time_chunks=chunks)
+    ms, Ps, ell = kalman.filtering(dev(ys, dtype), glg, chunks > 1, time_chunks=chunks,
+                                   f_diagonal=(fkind == "diag-shared"))
     r = TOL[dtype]["rtol"]
     npt.assert_allclose(host(ms), ems, rtol=r, atol=r * max(1.0, np.abs(ems).max()))
     npt.assert_allclose(host(Ps), ePs, rtol=r, atol=r * np.abs(ePs).max())
@@ -293,6 +294,8 @@ def test_sampling_time_invariant_diagonal_F(dtype, d, T, C):
     exs = ok.sampling(eps, ms, Ps, lg, False)
     glg = [dev(a, dtype) for a in lg]
     glg[2] = dev(F[None], dtype)
-    xs = kalman.sampling(dev(eps, dtype), dev(ms, dtype), dev(Ps, dtype), glg, False)
-    r = TOL[dtype]["rtol"]
-    npt.assert_allclose(host(xs), exs, rtol=r, atol=r * max(1.0, np.abs(exs).max()) * (10 if dtype == torch.float32 else 1))
+    for hint in (False, True):
+        xs = kalman.sampling(dev(eps, dtype), dev(ms, dtype), dev(Ps, dtype), glg, False, f_diagonal=hint)
+        r = TOL[dtype]["rtol"]
+        npt.assert_allclose(host(xs), exs, rtol=r,
+                            atol=r * max(1.0, np.abs(exs).max()) * (10 if dtype == torch.float32 else 1))
