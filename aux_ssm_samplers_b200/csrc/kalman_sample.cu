@@ -49,11 +49,18 @@ template <int D> __host__ __device__ constexpr size_t samp_smem_elems(bool lean)
 
 // In-place lower Cholesky with the reference's nan_to_num semantics: jnp.linalg.cholesky returns an
 // all-NaN factor when it fails, which nan_to_num turns into the zero matrix (sampling.py:102-104).
-template <typename T, int D> __device__ __forceinline__ void chol_nan_to_zero(T* A, T* dg, int n) {
+template <typename T, int D, bool PADDED = false>
+__device__ __forceinline__ void chol_nan_to_zero(T* A, T* dg, int n) {
   constexpr int LD = Tile<D>::LD;
-  chol_inplace<T, D>(A, dg, n);
+  chol_inplace<T, D, PADDED>(A, dg, n);
   bool bad = false;
-  for (int i = 0; i < n; ++i) bad = bad || !(dg[i] > T(0)) || !finite_(dg[i]);
+  if constexpr (Tile<D>::NT == 32) {
+    const int l = threadIdx.x;
+    const bool mine = (l < n) && (!(dg[l < n ? l : 0] > T(0)) || !finite_(dg[l < n ? l : 0]));
+    bad = __any_sync(0xffffffffu, mine) != 0;
+  } else {
+    for (int i = 0; i < n; ++i) bad = bad || !(dg[i] > T(0)) || !finite_(dg[i]);
+  }
   if (n == 1) bad = !finite_(dg[0]);  // scalar branch of the reference is a plain sqrt
   if (bad) {
     AUXSSM_FOR_ROWS(i, j, n, n) A[i * LD + j] = T(0);
@@ -64,7 +71,7 @@ template <typename T, int D> __device__ __forceinline__ void chol_nan_to_zero(T*
 // B <- L^{-T} B for the n x m block (thread j owns column j), right-looking: for i = n-1..0
 //   z_i = b_i / L_ii ;  b_k -= L_ik z_i  (k < i)      -- uses ROW i of L, i.e. broadcast vector loads.
 // dg = the workspace filled by the factorisation.  Register-resident for D <= 32.
-template <typename T, int D>
+template <typename T, int D, bool PADDED = false>
 __device__ __forceinline__ void bwd_solve(const T* L, T* B, const T* dg, int n, int m) {
   constexpr int LD = Tile<D>::LD;
   cta_sync<D>();
@@ -75,10 +82,10 @@ __device__ __forceinline__ void bwd_solve(const T* L, T* B, const T* dg, int n, 
       const T* dginv = dg + D;
       T z[D];
 #pragma unroll
-      for (int i = 0; i < D; ++i) z[i] = (i < n) ? B[i * LD + j] : T(0);
+      for (int i = 0; i < D; ++i) z[i] = (PADDED || i < n) ? B[i * LD + j] : T(0);
 #pragma unroll
       for (int i = D - 1; i >= 0; --i) {
-        if (i < n) {
+        if (PADDED || i < n) {
           const T zi = z[i] * dginv[i];
           z[i] = zi;
           B[i * LD + j] = zi;
@@ -118,6 +125,14 @@ __global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) sample_elements_
   s.m = p; p += D; s.bv = p; p += D; s.eps = p; p += D; s.r = p; p += D; s.e = p; p += D;
   T* fd = p; p += D;  // diag(F) (LEAN)
   s.dg = p;
+  constexpr bool PAD = LEAN && (D <= 32);
+  if (PAD) {  // identity on the padded diagonal of S and P: factorisations / solves run guard-free over D
+    if (threadIdx.x >= a.d.dx && threadIdx.x < D) {
+      s.S[threadIdx.x * LD + threadIdx.x] = T(1);
+      s.P[threadIdx.x * LD + threadIdx.x] = T(1);
+    }
+    __syncthreads();
+  }
   const int ul = blockIdx.x, unit = a.unit0 + ul;
   const int c = unit / a.d.n_batch, b = unit % a.d.n_batch;
   const int dx = a.d.dx, Tn = a.d.T, ssz = dx * dx + dx;
@@ -136,8 +151,8 @@ __global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) sample_elements_
     load_mat<T, D, false>(a.Ps + unit_off(a.d.Ps, c, b) + (int64_t)t * a.d.Ps.time, s.P, dx, dx);
     if (t == Tn - 1) {
       // last step: x_{T-1} = m + chol(P) eps  (sampling.py:116-124)
-      chol_nan_to_zero<T, D>(s.P, s.dg, dx);
-      mv_nn<T, D, 1>(s.P, s.eps, s.e, s.m, dx, dx);
+      chol_nan_to_zero<T, D, PAD>(s.P, s.dg, dx);
+      if (PAD) mv_nn_pad<T, D, 1>(s.P, s.eps, s.e, s.m); else mv_nn<T, D, 1>(s.P, s.eps, s.e, s.m, dx, dx);
       if (i < dx) g[dx * dx + i] = s.e[i];
       continue;
     }
@@ -188,13 +203,18 @@ __global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) sample_elements_
         mv_tn<T, D, 1>(s.Ft, s.m, s.r, s.bv, dx, dx);  // r = F m + b
       }
     }
-    chol_inplace<T, D>(s.S, s.dg, dx);
-    fwd_solve<T, D>(s.S, s.Z, nullptr, dx, dx, s.dg);  // Zs = Ls^{-1} F P
-    mm_tn<T, D, 2>(s.Z, s.Z, s.P, s.P, dx);            // Sigma = P - Zs^T Zs  (lower triangle feeds the Cholesky)
-    bwd_solve<T, D>(s.S, s.Z, s.dg, dx, dx);           // Z <- G^T = Ls^{-T} Zs
-    chol_nan_to_zero<T, D>(s.P, s.dg, dx);             // L = chol(Sigma), NaN -> 0
-    mv_tn<T, D, 2>(s.Z, s.r, s.e, s.m, dx, dx);        // e = m - G (F m + b)     (G v = (G^T)^T v)
-    mv_nn<T, D, 1>(s.P, s.eps, s.e, s.e, dx, dx);      // e += L eps
+    chol_inplace<T, D, PAD>(s.S, s.dg, dx);
+    fwd_solve<T, D, PAD>(s.S, s.Z, nullptr, dx, dx, s.dg);  // Zs = Ls^{-1} F P
+    mm_tn<T, D, 2>(s.Z, s.Z, s.P, s.P, PAD ? D : dx);       // Sigma = P - Zs^T Zs  (lower triangle feeds the Cholesky)
+    bwd_solve<T, D, PAD>(s.S, s.Z, s.dg, dx, dx);           // Z <- G^T = Ls^{-T} Zs
+    chol_nan_to_zero<T, D, PAD>(s.P, s.dg, dx);             // L = chol(Sigma), NaN -> 0
+    if (PAD) {
+      mv_tn_pad<T, D, 2>(s.Z, s.r, s.e, s.m);               // e = m - G (F m + b)     (G v = (G^T)^T v)
+      mv_nn_pad<T, D, 1>(s.P, s.eps, s.e, s.e);             // e += L eps
+    } else {
+      mv_tn<T, D, 2>(s.Z, s.r, s.e, s.m, dx, dx);
+      mv_nn<T, D, 1>(s.P, s.eps, s.e, s.e, dx, dx);
+    }
     store_mat<T, D>(g, s.Z, dx, dx);
     if (i < dx) g[dx * dx + i] = s.e[i];
   }

@@ -145,9 +145,12 @@ template <typename T, int D> __device__ __forceinline__ void zero_mat(T* A) {
 
 // ---- element-wise helpers: warp w owns rows w, w + NW, ...; lanes run over columns.  No integer
 // division, global accesses are row-contiguous (coalesced), shared accesses are conflict-free.
-#define AUXSSM_FOR_ROWS(r, c, rows, cols)                                             \
-  for (int r = (int)(threadIdx.x >> 5); r < (rows); r += Tile<D>::NT / 32)           \
-    for (int c = (int)(threadIdx.x & 31); c < (cols); c += 32)
+// For D <= 32 a row fits one warp pass: the column loop runs at most once, which the compiler can turn
+// into a predicate (no divergence bookkeeping); the row loop is unrolled by four.
+#define AUXSSM_FOR_ROWS(r, c, rows, cols)                                                   \
+  _Pragma("unroll 4")                                                                       \
+  for (int r = (int)(threadIdx.x >> 5); r < (rows); r += Tile<D>::NT / 32)                 \
+    for (int c = (int)(threadIdx.x & 31), once_ = 1; once_ && c < (cols); once_ = (D > 32), c += 32)
 
 // dst = src^T: dst[j][i] = src[i][j] for i < rows, j < cols, zero elsewhere (whole D x D tile).
 template <typename T, int D> __device__ __forceinline__ void transpose_to(const T* src, T* dst, int rows, int cols) {
@@ -237,7 +240,8 @@ __device__ __forceinline__ void store_mat_t(T* __restrict__ g, const T* s, int r
 // ~35 cycles instead of sqrt + divide on the serial critical path); NaN for x < 0, like sqrt.
 template <typename T> __device__ __forceinline__ void pivot_(T x, T& l, T& inv);
 template <> __device__ __forceinline__ void pivot_<float>(float x, float& l, float& inv) {
-  float r = rsqrtf(x);
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // one MUFU.RSQ, no denormal fix-up code
   r = r * fmaf(-0.5f * x, r * r, 1.5f);
   inv = r;
   l = (x == 0.f) ? 0.f : x * r;
@@ -251,7 +255,9 @@ template <> __device__ __forceinline__ void pivot_<double>(double x, double& l, 
 // scaled column k is exchanged through a double-buffered shared vector (one STS + (D-k)/4 broadcast
 // LDS.128 per column, __syncwarp only).  `dg` receives diag(L), `dginv` (optional) its reciprocal.
 // `colbuf` needs 2*D words.  All D x D loops are fully unrolled so the row stays in registers.
-template <typename T, int D>
+// PADDED = the caller keeps an identity block on the padded diagonal (rows/cols >= n), so all D columns
+// can be processed without any run-time guard (branch-free, ~20% fewer instructions at d = 30).
+template <typename T, int D, bool PADDED = false>
 __device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n) {
   constexpr int LD = Tile<D>::LD;
   constexpr int V = (D >= 4) ? 4 : D;
@@ -264,11 +270,11 @@ __device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n
       T tmp[V];
       if (lane < D) ldv<T, V>(tmp, A + lane * LD + j);
 #pragma unroll
-      for (int q = 0; q < V; ++q) row[j + q] = (lane < n) ? tmp[q] : T(0);
+      for (int q = 0; q < V; ++q) row[j + q] = (PADDED || lane < n) ? tmp[q] : T(0);
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      if (k < n) {
+      if (PADDED || k < n) {
         const T akk = __shfl_sync(0xffffffffu, row[k], k);
         T lkk, inv;
         pivot_<T>(akk, lkk, inv);
@@ -291,7 +297,7 @@ __device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n
         }
       }
     }
-    if (lane < n) {
+    if ((PADDED && lane < D) || lane < n) {
 #pragma unroll
       for (int j = 0; j < D; j += V) {
         T tmp[V];
@@ -307,7 +313,7 @@ __device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n
 // Register-resident forward substitution for D <= 32: thread j owns column j of B (n x m) in
 // registers, rows of L are read as broadcast vector loads, two accumulators per dot product.
 // `dginv` = 1 / diag(L).  Thread m handles the optional extra vector `bvec`.
-template <typename T, int D>
+template <typename T, int D, bool PADDED = false>
 __device__ __forceinline__ void fwd_solve_reg(const T* L, T* B, T* bvec, const T* dginv, int n, int m) {
   constexpr int LD = Tile<D>::LD;
   constexpr int V = (D >= 4) ? 4 : D;
@@ -329,7 +335,7 @@ __device__ __forceinline__ void fwd_solve_reg(const T* L, T* B, T* bvec, const T
     T z[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      if (i < n) {
+      if (PADDED || i < n) {
         T acc0 = is_vec ? bvec[i] : B[i * LD + j];
         T acc1 = T(0);
 #pragma unroll
@@ -406,16 +412,68 @@ template <typename T, int D> __device__ __forceinline__ void fwd_solve_generic(c
 template <int D> struct CholWs { static constexpr int WORDS = 4 * D; };
 
 // In-place lower Cholesky of the n x n block; strict upper triangle zeroed; non-PD pivots give NaN.
-template <typename T, int D> __device__ __forceinline__ void chol_inplace(T* A, T* dg, int n) {
-  if constexpr (D <= 32) chol_reg<T, D>(A, dg, dg + D, dg + 2 * D, n);
+template <typename T, int D, bool PADDED = false> __device__ __forceinline__ void chol_inplace(T* A, T* dg, int n) {
+  if constexpr (D <= 32) chol_reg<T, D, PADDED>(A, dg, dg + D, dg + 2 * D, n);
   else chol_generic<T, D>(A, dg, n);
 }
 // Z = L^{-1} B in place (n x m block) and optionally bvec <- L^{-1} bvec; `dg` is the workspace the
 // factorisation of L filled.
-template <typename T, int D>
+template <typename T, int D, bool PADDED = false>
 __device__ __forceinline__ void fwd_solve(const T* L, T* B, T* bvec, int n, int m, const T* dg) {
-  if constexpr (D <= 32) fwd_solve_reg<T, D>(L, B, bvec, dg + D, n, m);
+  if constexpr (D <= 32) fwd_solve_reg<T, D, PADDED>(L, B, bvec, dg + D, n, m);
   else fwd_solve_generic<T, D>(L, B, bvec, n, m);
+}
+
+// Branch-free matrix-vector products over the whole padded tile (operands zero beyond their logical size):
+// y = e (+|-) A^T x   (A k-major)  and  y = e (+) A x  (A row-major).  MODE as mm_tn.  D <= 32 (one value per thread).
+template <typename T, int D, int MODE>
+__device__ __forceinline__ void mv_tn_pad(const T* A, const T* x, T* y, const T* e) {
+  constexpr int LD = Tile<D>::LD, V = (D >= 4) ? 4 : D;
+  cta_sync<D>();
+  const int i = threadIdx.x;
+  T out = T(0);
+  if (i < D) {
+    T a0 = T(0), a1 = T(0);
+#pragma unroll
+    for (int k = 0; k < D; k += V) {
+      T xv[V];
+      ldv<T, V>(xv, x + k);
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        if (q & 1) a1 = fma_(A[(k + q) * LD + i], xv[q], a1); else a0 = fma_(A[(k + q) * LD + i], xv[q], a0);
+      }
+    }
+    const T acc = a0 + a1;
+    out = (MODE == 0) ? acc : (MODE == 1 ? e[i] + acc : e[i] - acc);
+  }
+  cta_sync<D>();
+  if (i < D) y[i] = out;
+  cta_sync<D>();
+}
+template <typename T, int D, int MODE>
+__device__ __forceinline__ void mv_nn_pad(const T* A, const T* x, T* y, const T* e) {
+  constexpr int LD = Tile<D>::LD, V = (D >= 4) ? 4 : D;
+  cta_sync<D>();
+  const int i = threadIdx.x;
+  T out = T(0);
+  if (i < D) {
+    T a0 = T(0), a1 = T(0);
+#pragma unroll
+    for (int k = 0; k < D; k += V) {
+      T xv[V], av[V];
+      ldv<T, V>(xv, x + k);
+      ldv<T, V>(av, A + i * LD + k);
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        if (q & 1) a1 = fma_(av[q], xv[q], a1); else a0 = fma_(av[q], xv[q], a0);
+      }
+    }
+    const T acc = a0 + a1;
+    out = (MODE == 0) ? acc : (MODE == 1 ? e[i] + acc : e[i] - acc);
+  }
+  cta_sync<D>();
+  if (i < D) y[i] = out;
+  cta_sync<D>();
 }
 
 // X = (L L^T)^{-1} B in place (n x m block, thread j owns column j).
