@@ -210,7 +210,7 @@ template <typename T, int OP>
 __global__ void __launch_bounds__(1024) csmc_primitive_kernel(int N, const T* __restrict__ in, const T* __restrict__ u,
                                                               const T* __restrict__ u_kill, T* __restrict__ wout,
                                                               int32_t* __restrict__ idx) {
-  __shared__ T red[32];
+  __shared__ T red[64];
   __shared__ T cdf[1024];
   const int64_t row = blockIdx.x;
   const int i = threadIdx.x;

@@ -36,32 +36,33 @@ template <typename T> __device__ __forceinline__ T log_2pi_half() { return T(0.9
 
 template <typename T> __device__ __forceinline__ T block_max(T v, T* red) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncwarp();
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
   if (lane == 0) red[w] = v;
   __syncthreads();
   T m = red[0];
   for (int g = 1; g < nw; ++g) m = fmax(m, red[g]);
-  __syncthreads();
-  return m;
+  return m;  // no trailing barrier: `red` must not be rewritten before another barrier has been passed
 }
 
 // xor butterfly inside each warp, warp totals added serially in warp order (matches oracle.canonical_sum)
 template <typename T> __device__ __forceinline__ T block_sum(T v, T* red) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncwarp();
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
   if (lane == 0) red[w] = v;
   __syncthreads();
   T s = red[0];
   for (int g = 1; g < nw; ++g) s = s + red[g];
-  __syncthreads();
   return s;
 }
 
 // Hillis-Steele inclusive scan inside each warp, serial warp offsets (matches oracle.canonical_cdf)
 template <typename T> __device__ __forceinline__ T block_cdf(T v, T* red) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncwarp();
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
     const T o = __shfl_up_sync(0xffffffffu, v, off);
@@ -71,16 +72,16 @@ template <typename T> __device__ __forceinline__ T block_cdf(T v, T* red) {
   __syncthreads();
   T offs = T(0);
   for (int g = 1; g <= w; ++g) offs = offs + red[g - 1];
-  __syncthreads();
   return v + offs;
 }
 
 // w = exp(lw - logsumexp(lw)) over the N active threads (math/utils.py:24-39)
+// `red` holds 2 x 32 words (one per reduction).
 template <typename T> __device__ __forceinline__ T block_normalize(T lw, bool active, T* red) {
   T amax = block_max<T>(active ? lw : -INFINITY, red);
   if (!isfinite(amax)) amax = T(0);
   const T e = active ? exp(lw - amax) : T(0);
-  const T s = block_sum<T>(e, red);
+  const T s = block_sum<T>(e, red + 32);
   const T lse = log(s) + amax;
   return active ? exp(lw - lse) : T(0);
 }
@@ -266,7 +267,7 @@ __device__ __forceinline__ T propose_and_weight(const auxssm_csmc_desc& dsc, con
 
 template <int D> __host__ __device__ inline size_t csmc_smem_elems(int N, int d, int prop) {
   const size_t mats = (prop == AUXSSM_PROP_GUIDED) ? 5 : 3;
-  return mats * D * D + 16 * D + 2 * (size_t)N * d + N + 64;
+  return mats * D * D + 16 * D + 2 * (size_t)N * d + N + 256;
 }
 
 // Loads a [d x d] row-major global matrix into a D x D zero-padded shared image.
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
   if (PROP == AUXSSM_PROP_GUIDED) { m.K = p; p += D * D; m.cL = p; p += D * D; }
   m.b = p; p += D; m.m0 = p; p += D; m.invq = p; p += D; m.invp0 = p; p += D; m.invl = p; p += D;
   m.y = p; p += D; m.xs_t = p; p += D; m.u_t = p; p += D; m.mean_t = p; p += D; m.xsel = p; p += D;
-  T* red = p; p += 32;
+  T* red = p; p += 128;  // 4 x 32: max, sum, cdf, killing-max (never reused without a barrier in between)
   T* misc = p; p += 32;  // misc[0]: max weight (killing); misc[8..]: selected index as int
   int* isel = reinterpret_cast<int*>(misc + 8);
   T* cdf = p; p += N;
@@ -338,6 +339,36 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
     T xn[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) xn[k] = T(0);
+    // Software pipeline: the draws and per-step parameters of step t+1 are requested at the top of step t,
+    // so no DRAM round trip sits on the (strictly sequential) critical path of the time loop.
+    constexpr bool DIRECT = (D <= 4);  // normals read straight into registers (coalesced for small d)
+    T ur_n = T(0), uk_n = T(0), eps_n[D], xs_n = T(0), y_n = T(0), u_n = T(0), g_n = T(0), s_n = T(1);
+#pragma unroll
+    for (int k = 0; k < D; ++k) eps_n[k] = T(0);
+    auto prefetch = [&](int tt) {  // everything step tt needs
+      const bool go = tt < Tn;
+      if (go && active) {
+        if (tt > 0) {
+          ur_n = a.u_res[((int64_t)c * (Tn - 1) + (tt - 1)) * N + i];
+          if (dsc.resampling == AUXSSM_RESAMPLE_KILLING) uk_n = a.u_kill[((int64_t)c * (Tn - 1) + (tt - 1)) * N + i];
+        }
+        if (DIRECT) {
+          const T* eg = a.normals + (((int64_t)c * Tn + tt) * N + i) * d;
+#pragma unroll
+          for (int k = 0; k < D; ++k) if (k < d) eps_n[k] = eg[k];
+        }
+      }
+      if (go && i < D) {
+        xs_n = (i < d) ? xstar[(int64_t)tt * d + i] : T(0);
+        if (ysc) y_n = (i < d) ? ysc[(int64_t)tt * d + i] : T(0);
+        if (PROP != AUXSSM_PROP_BOOTSTRAP) {
+          u_n = (i < d) ? a.u[((int64_t)c * Tn + tt) * d + i] : T(0);
+          g_n = (a.grad != nullptr && i < d) ? a.grad[((int64_t)c * Tn + tt) * d + i] : T(0);
+        }
+      }
+      if (go && PROP != AUXSSM_PROP_BOOTSTRAP) s_n = a.shd[(int64_t)c * Tn + tt];
+    };
+    prefetch(0);
 
     // ------------------------------ forward conditional particle filter ------------------------------
     for (int t = 0; t < Tn; ++t) {
@@ -347,48 +378,53 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
       T xp[D];
 #pragma unroll
       for (int k = 0; k < D; ++k) xp[k] = T(0);
+      // take this step's prefetched values, then request the next step's
+      const T ur = ur_n, uk = uk_n, xs_c = xs_n, y_c = y_n, u_c = u_n, g_c = g_n, s_c = s_n;
+      T eps[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) eps[k] = eps_n[k];
+      prefetch(t + 1);
       if (!first && active) {
-        const T ur = a.u_res[((int64_t)c * (Tn - 1) + (t - 1)) * N + i];
         const T r = cdf[N - 1] * (T(1) - ur);
         anc = search_left<T>(cdf, r, N);
-        if (dsc.resampling == AUXSSM_RESAMPLE_KILLING) {
-          const T uk = a.u_kill[((int64_t)c * (Tn - 1) + (t - 1)) * N + i];
-          // survive iff u_kill * max_j w_j < w_i  (max weight of the previous step kept in misc[0])
-          if (uk * misc[0] < w) anc = i;
-        }
+        // killing: survive iff u_kill * max_j w_j < w_i  (max weight of the previous step kept in misc[0])
+        if (dsc.resampling == AUXSSM_RESAMPLE_KILLING && uk * misc[0] < w) anc = i;
         if (i == 0) anc = 0;
 #pragma unroll
         for (int k = 0; k < D; ++k) if (k < d) xp[k] = part[anc * d + k];
       }
-      __syncthreads();  // every parent gathered before `part` is overwritten
-      // (3) per-step parameters
+      // (3) per-step parameters -> shared (read after the barrier below)
       if (i < D) {
-        m.xs_t[i] = (i < d) ? xstar[(int64_t)t * d + i] : T(0);
-        if (ysc) m.y[i] = (i < d) ? ysc[(int64_t)t * d + i] : T(0);
+        m.xs_t[i] = xs_c;
+        if (ysc) m.y[i] = y_c;
         if (PROP != AUXSSM_PROP_BOOTSTRAP) {
-          const T s = a.shd[(int64_t)c * Tn + t];
-          const T uu = (i < d) ? a.u[((int64_t)c * Tn + t) * d + i] : T(0);
-          const T gg = (a.grad != nullptr && i < d) ? a.grad[((int64_t)c * Tn + t) * d + i] : T(0);
-          m.u_t[i] = uu;
-          m.mean_t[i] = uu + s * s * gg;
+          m.u_t[i] = u_c;
+          m.mean_t[i] = u_c + s_c * s_c * g_c;
         }
       }
-      if (PROP != AUXSSM_PROP_BOOTSTRAP) m.s_t = a.shd[(int64_t)c * Tn + t];
-      if (PROP == AUXSSM_PROP_GUIDED && (t <= 1 || dsc.gains_time_stride != 0)) {
+      if (PROP != AUXSSM_PROP_BOOTSTRAP) m.s_t = s_c;
+      if (!DIRECT) {
+        __syncthreads();  // every parent gathered before `stage` / `part` are overwritten
+        if (PROP == AUXSSM_PROP_GUIDED && (t <= 1 || dsc.gains_time_stride != 0)) {
+          load_padded<T, D>(a.K + (int64_t)t * dsc.gains_time_stride, m.K, d);
+          load_padded<T, D>(a.cL + (int64_t)t * dsc.gains_time_stride, m.cL, d);
+        }
+        // normals of this step, staged with coalesced loads
+        const T* eg = a.normals + ((int64_t)c * Tn + t) * N * d;
+        for (int e = i; e < N * d; e += blockDim.x) stage[e] = eg[e];
+      } else if (PROP == AUXSSM_PROP_GUIDED && (t <= 1 || dsc.gains_time_stride != 0)) {
         load_padded<T, D>(a.K + (int64_t)t * dsc.gains_time_stride, m.K, d);
         load_padded<T, D>(a.cL + (int64_t)t * dsc.gains_time_stride, m.cL, d);
       }
-      // normals of this step, staged with coalesced loads
-      const T* eg = a.normals + ((int64_t)c * Tn + t) * N * d;
-      for (int e = i; e < N * d; e += blockDim.x) stage[e] = eg[e];
-      __syncthreads();
+      __syncthreads();  // parents gathered, parameters / staged normals visible
       if (PROP == AUXSSM_PROP_GUIDED && (t <= 1 || dsc.gains_time_stride != 0)) {
         m.cst_l = factor_consts<T, D>(m.cL, m.invl, d);
         __syncthreads();
       }
-      T eps[D];
+      if (!DIRECT) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) eps[k] = (active && k < d) ? stage[i * d + k] : T(0);
+        for (int k = 0; k < D; ++k) eps[k] = (active && k < d) ? stage[i * d + k] : T(0);
+      }
       // (4) propose, pin particle 0 to the reference trajectory, (5) weight
       T lw = propose_and_weight<T, D, PROP>(dsc, m, first, i == 0, xp, eps, xn);
       if (active) {
@@ -403,10 +439,10 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
       for (int e = i; e < N * d; e += blockDim.x) xg[e] = part[e];
       // (7) normalise, CDF
       w = block_normalize<T>(lw, active, red);
-      const T cd = block_cdf<T>(w, red);
+      const T cd = block_cdf<T>(w, red + 64);
       if (active) cdf[i] = cd;
       if (dsc.resampling == AUXSSM_RESAMPLE_KILLING) {
-        const T wmax = block_max<T>(w, red);
+        const T wmax = block_max<T>(w, red + 96);
         if (i == 0) misc[0] = wmax;
       }
       __syncthreads();
@@ -433,27 +469,51 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
       __syncthreads();
     }
     if (dsc.backward) {
-      for (int t = Tn - 2, k2 = 1; t >= 0; --t, ++k2) {
-        // history of step t, staged with coalesced loads
-        const T* xg = xs_h + (int64_t)t * N * d;
-        for (int e = i; e < N * d; e += blockDim.x) stage[e] = xg[e];
-        __syncthreads();
-        T xt[D], xpred[D], xsel[D];
+      // history of step t-1 is requested while step t is processed (registers, small d)
+      T xt_n[D], lwh_n = T(0);
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-          xt[k] = (active && k < d) ? stage[i * d + k] : T(0);
-          xsel[k] = m.xsel[k];
+      for (int k = 0; k < D; ++k) xt_n[k] = T(0);
+      auto bprefetch = [&](int tt) {
+        if (tt >= 0 && active) {
+          const T* xg = xs_h + ((int64_t)tt * N + i) * d;
+#pragma unroll
+          for (int k = 0; k < D; ++k) if (k < d) xt_n[k] = xg[k];
+          lwh_n = lw_h[(int64_t)tt * N + i];
         }
+      };
+      constexpr bool BDIRECT = DIRECT && sizeof(T) == 4;  // register prefetch of the history (fp32 path)
+      if (BDIRECT) bprefetch(Tn - 2);
+      T ub_n = (Tn > 1) ? ub[1] : T(0);
+      for (int t = Tn - 2, k2 = 1; t >= 0; --t, ++k2) {
+        T xt[D], xpred[D], xsel[D];
+        T lwh = T(0);
+        const T ub_c = ub_n;
+        if (t > 0) ub_n = ub[k2 + 1];
+        if (BDIRECT) {
+#pragma unroll
+          for (int k = 0; k < D; ++k) xt[k] = xt_n[k];
+          lwh = lwh_n;
+          bprefetch(t - 1);
+        } else {
+          // history of step t, staged with coalesced loads
+          const T* xg = xs_h + (int64_t)t * N * d;
+          for (int e = i; e < N * d; e += blockDim.x) stage[e] = xg[e];
+          __syncthreads();
+#pragma unroll
+          for (int k = 0; k < D; ++k) xt[k] = (active && k < d) ? stage[i * d + k] : T(0);
+          if (active) lwh = lw_h[(int64_t)t * N + i];
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) xsel[k] = m.xsel[k];
         matvec<T, D>(m.F, xt, xpred);
 #pragma unroll
         for (int k = 0; k < D; ++k) xpred[k] += m.b[k];
-        T lw = prior_logpdf<T, D>(m, false, xsel, xpred);
-        if (active) lw += lw_h[(int64_t)t * N + i];
+        T lw = prior_logpdf<T, D>(m, false, xsel, xpred) + lwh;
         const T wb = block_normalize<T>(lw, active, red);
-        const T cd = block_cdf<T>(wb, red);
+        const T cd = block_cdf<T>(wb, red + 64);
         if (active) cdf[i] = cd;
         __syncthreads();
-        const T r = cdf[N - 1] * (T(1) - ub[k2]);
+        const T r = cdf[N - 1] * (T(1) - ub_c);
         int B = __syncthreads_count(active && cdf[i] < r);
         if (B > N - 1) B = N - 1;
         __syncthreads();  // everyone has read m.xsel / cdf before they change
