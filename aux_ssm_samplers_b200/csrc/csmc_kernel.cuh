@@ -32,7 +32,10 @@ template <typename T> struct CsmcArgs {
 
 template <typename T> __device__ __forceinline__ T log_2pi_half() { return T(0.91893853320467274178); }
 
-// ---- canonical block reductions (blockDim.x a multiple of 32) ---------------------------------------
+// ---- canonical block reductions (blockDim.x a multiple of 32, at most 32 warps) ---------------------
+// Two levels of the same 32-wide pattern: inside each warp, then across the (zero-padded) 32 warp totals,
+// which every warp recomputes redundantly with shuffles (no serial loop over warps).
+// `red` is a 32-word buffer that must not be rewritten before another barrier has been passed.
 
 template <typename T> __device__ __forceinline__ T block_max(T v, T* red) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -41,12 +44,14 @@ template <typename T> __device__ __forceinline__ T block_max(T v, T* red) {
   for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
   if (lane == 0) red[w] = v;
   __syncthreads();
-  T m = red[0];
-  for (int g = 1; g < nw; ++g) m = fmax(m, red[g]);
-  return m;  // no trailing barrier: `red` must not be rewritten before another barrier has been passed
+  T m = (lane < nw) ? red[lane] : -INFINITY;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+  return m;
 }
 
-// xor butterfly inside each warp, warp totals added serially in warp order (matches oracle.canonical_sum)
+// xor butterfly (16, 8, 4, 2, 1) inside each warp, then the same butterfly over the warp totals
+// (matches oracle.canonical_sum)
 template <typename T> __device__ __forceinline__ T block_sum(T v, T* red) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   __syncwarp();
@@ -54,14 +59,16 @@ template <typename T> __device__ __forceinline__ T block_sum(T v, T* red) {
   for (int off = 16; off > 0; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
   if (lane == 0) red[w] = v;
   __syncthreads();
-  T s = red[0];
-  for (int g = 1; g < nw; ++g) s = s + red[g];
+  T s = (lane < nw) ? red[lane] : T(0);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
   return s;
 }
 
-// Hillis-Steele inclusive scan inside each warp, serial warp offsets (matches oracle.canonical_cdf)
+// Hillis-Steele inclusive scan (1, 2, 4, 8, 16) inside each warp, the same scan over the warp totals gives
+// the warp offsets, one add of the offset (matches oracle.canonical_cdf)
 template <typename T> __device__ __forceinline__ T block_cdf(T v, T* red) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   __syncwarp();
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
@@ -70,9 +77,15 @@ template <typename T> __device__ __forceinline__ T block_cdf(T v, T* red) {
   }
   if (lane == 31) red[w] = v;
   __syncthreads();
-  T offs = T(0);
-  for (int g = 1; g <= w; ++g) offs = offs + red[g - 1];
-  return v + offs;
+  T tot = (lane < nw) ? red[lane] : T(0);
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const T o = __shfl_up_sync(0xffffffffu, tot, off);
+    if (lane >= off) tot = tot + o;
+  }
+  // inclusive scan of the warp totals; the offset of warp w is the inclusive value of warp w - 1
+  const T offs = __shfl_sync(0xffffffffu, tot, (w > 0) ? w - 1 : 0);
+  return (w > 0) ? v + offs : v;
 }
 
 // w = exp(lw - logsumexp(lw)) over the N active threads (math/utils.py:24-39)
@@ -469,39 +482,20 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
       __syncthreads();
     }
     if (dsc.backward) {
-      // history of step t-1 is requested while step t is processed (registers, small d)
-      T xt_n[D], lwh_n = T(0);
-#pragma unroll
-      for (int k = 0; k < D; ++k) xt_n[k] = T(0);
-      auto bprefetch = [&](int tt) {
-        if (tt >= 0 && active) {
-          const T* xg = xs_h + ((int64_t)tt * N + i) * d;
-#pragma unroll
-          for (int k = 0; k < D; ++k) if (k < d) xt_n[k] = xg[k];
-          lwh_n = lw_h[(int64_t)tt * N + i];
-        }
-      };
-      constexpr bool BDIRECT = DIRECT && sizeof(T) == 4;  // register prefetch of the history (fp32 path)
-      if (BDIRECT) bprefetch(Tn - 2);
       T ub_n = (Tn > 1) ? ub[1] : T(0);
       for (int t = Tn - 2, k2 = 1; t >= 0; --t, ++k2) {
         T xt[D], xpred[D], xsel[D];
         T lwh = T(0);
         const T ub_c = ub_n;
         if (t > 0) ub_n = ub[k2 + 1];
-        if (BDIRECT) {
-#pragma unroll
-          for (int k = 0; k < D; ++k) xt[k] = xt_n[k];
-          lwh = lwh_n;
-          bprefetch(t - 1);
-        } else {
+        {
           // history of step t, staged with coalesced loads
           const T* xg = xs_h + (int64_t)t * N * d;
           for (int e = i; e < N * d; e += blockDim.x) stage[e] = xg[e];
+          if (active) lwh = lw_h[(int64_t)t * N + i];
           __syncthreads();
 #pragma unroll
           for (int k = 0; k < D; ++k) xt[k] = (active && k < d) ? stage[i * d + k] : T(0);
-          if (active) lwh = lw_h[(int64_t)t * N + i];
         }
 #pragma unroll
         for (int k = 0; k < D; ++k) xsel[k] = m.xsel[k];

@@ -24,9 +24,9 @@ Every ``jax.random`` draw is an explicit argument:
 CANONICAL SUMMATION ORDER.  Ancestor indices depend on the floating-point order in which the CDF
 is accumulated, and XLA's ``cumsum`` order is unspecified.  Oracle and CUDA kernels therefore share
 one fixed order (``canonical_cdf`` / ``canonical_sum`` below): an inclusive Hillis--Steele scan
-inside each group of 32 consecutive particles (offsets 1, 2, 4, 8, 16), group totals accumulated
-serially, one add of the group offset; sums use the xor-butterfly (16, 8, 4, 2, 1) inside groups of
-32 and a serial sum over groups.  ``mismatches_vs_plain_cumsum`` reports how often a plain
+inside each group of 32 consecutive particles (offsets 1, 2, 4, 8, 16), the same scan over the
+(zero-padded) group totals for the group offsets, one add of the group offset; sums use the
+xor-butterfly (16, 8, 4, 2, 1) inside groups of 32 and the same butterfly over the group totals.  ``mismatches_vs_plain_cumsum`` reports how often a plain
 ``np.cumsum`` CDF would have picked a different index.
 
 Parity status: multinomial index-0 pin / frequencies and systematic == Chopin--Singh Alg. 4 are
@@ -55,36 +55,46 @@ def _pad32(a, fill):
 
 
 def canonical_sum(a):
-    """Sum over the last axis in the kernels' order (dtype preserved)."""
+    """Sum over the last axis in the kernels' order (dtype preserved): xor butterfly inside groups of 32,
+    then the same butterfly over the (zero-padded) group totals, recursively."""
     a = np.asarray(a)
-    n = a.shape[-1]
-    v = _pad32(a, 0).reshape(a.shape[:-1] + (-1, 32)).copy()
-    for off in (16, 8, 4, 2, 1):
-        v = v + v[..., _LANES ^ off]
-    tot = v[..., 0, 0].copy()
-    for g in range(1, v.shape[-2]):
-        tot = tot + v[..., g, 0]
-    return tot
+    while True:
+        v = _pad32(a, 0).reshape(a.shape[:-1] + (-1, 32)).copy()
+        for off in (16, 8, 4, 2, 1):
+            v = v + v[..., _LANES ^ off]
+        tot = v[..., 0]
+        if tot.shape[-1] == 1:
+            return tot[..., 0]
+        a = tot
 
 
 def canonical_max(a):
     return np.max(a, axis=-1)
 
 
-def canonical_cdf(w):
-    """Inclusive prefix sum over the last axis in the kernels' order (dtype preserved)."""
-    w = np.asarray(w)
-    n = w.shape[-1]
-    v = _pad32(w, 0).reshape(w.shape[:-1] + (-1, 32)).copy()
+def _scan32(v):
+    """Hillis--Steele inclusive scan over the last axis of a [..., 32] array."""
+    v = v.copy()
     for off in (1, 2, 4, 8, 16):
         shifted = np.zeros_like(v)
         shifted[..., off:] = v[..., :-off]
         v = np.where(_LANES >= off, v + shifted, v)
-    offs = np.zeros(v.shape[:-1], dtype=w.dtype)
-    for g in range(1, v.shape[-2]):
-        offs[..., g] = offs[..., g - 1] + v[..., g - 1, 31]
-    out = v + offs[..., None]
-    # group 0 is not offset (adding 0.0 is exact anyway)
+    return v
+
+
+def canonical_cdf(w):
+    """Inclusive prefix sum over the last axis in the kernels' order (dtype preserved): Hillis--Steele scan
+    inside groups of 32, the same scan over the (zero-padded) group totals gives the group offsets, one add
+    of the offset (group 0 is not offset).  Supports up to 1024 entries (32 groups), like the kernels."""
+    w = np.asarray(w)
+    n = w.shape[-1]
+    assert n <= 1024
+    v = _scan32(_pad32(w, 0).reshape(w.shape[:-1] + (-1, 32)))
+    ng = v.shape[-2]
+    tot = _scan32(_pad32(v[..., 31], 0))[..., :ng]      # inclusive scan of the group totals
+    out = v.copy()
+    if ng > 1:
+        out[..., 1:, :] = v[..., 1:, :] + tot[..., :-1, None]
     return out.reshape(w.shape[:-1] + (-1,))[..., :n]
 
 
