@@ -273,6 +273,18 @@ def run_gpu(args):
             survey_bytes_unit=(3 * d * d + 4 * d) * es,      # read 3d^2+3d, write d
             flops_unit=2 * (1.0 / 6 + 0.5 + 0.5 + 1 + 1.0 / 6) * d ** 3 + 2 * d * d),
     }
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))["per_launch"]
+    except Exception:
+        pass
+
+    def ncu_traffic(kernel_label):
+        for k, v in traffic.items():
+            if kernel_label.startswith(k.split("<")[0]):
+                return v["dram_read_bytes"] + v["dram_write_bytes"]
+        return None
+
     roofs = []
     for name, cnd in cands.items():
         calls, ms_tot = summ.get(name, (0, 0.0))
@@ -284,7 +296,8 @@ def run_gpu(args):
             "bound": "hbm", "kernel": cnd["kernel"] + " (" + name + ")", "achieved": ach, "peak": peak_hbm,
             "unit": "GB/s", "frac": ach / peak_hbm,
             "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-            "traffic": None, "ms_per_launch": per, "launches_timed": calls,
+            "traffic": ncu_traffic(cnd["kernel"]), "traffic_source": "profiles/traffic_r1.json (ncu --set full)",
+            "ms_per_launch": per, "launches_timed": calls,
             "alg_bytes_per_unit": cnd["bytes_unit"], "survey_bytes_per_unit": cnd["survey_bytes_unit"],
             "share_of_step": ms_tot / step_ms_local,
             "fp32_tflops_achieved": cnd["flops_unit"] * units_launch / (per * 1e-3) / 1e12,
