@@ -505,11 +505,12 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
   // inside the CTA, so single-warp CTAs would all queue on one scheduler.
   constexpr int GY = 4, GX = 8, TM = D / GY, TN = D / GX, LDS_ = D + 4, WPC = 4;
   __shared__ __align__(16) T stage_[WPC][D * LDS_];
-  __shared__ __align__(16) T rowbuf_[WPC][2 * (D + 4)];
-  __shared__ T ev_[WPC][D], rdv_[WPC][D], svbuf_[WPC][D], mvec_[WPC][D];
+  __shared__ __align__(16) T ev_[WPC][D];
+  __shared__ __align__(16) T rdv_[WPC][D];
+  __shared__ T svbuf_[WPC][D], mvec_[WPC][D];
   const int wq = threadIdx.x >> 5;
   T* stage = stage_[wq];
-  T* rowbuf = rowbuf_[wq];
+  T* rowbuf = stage_[wq];  // the row-exchange buffers alias the output stage (disjoint in time, __syncwarp between)
   T *ev = ev_[wq], *rdv = rdv_[wq], *svbuf = svbuf_[wq], *mvec = mvec_[wq];
   const int lane = threadIdx.x & 31, ty = lane / GX, tx = lane % GX;
   const int j = chunk_first + blockIdx.y, unit = blockIdx.x * WPC + wq;
@@ -591,36 +592,128 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
       }
     }
     __syncwarp();
-    // ---- d scalar measurement updates ----
+    // ---- measurement update: blocks of four scalar observations ----
+    // Four conditionally independent scalar observations are absorbed at once: the 4 x 4 innovation
+    // covariance S_b = P[I, I] + diag(r_I) is factorised redundantly by every lane in registers, Z = L_b^{-1} P[I, :]
+    // by forward substitution, P -= Z^T Z, m += Z^T L_b^{-1}(y_I - m_I).  Same algebra as d rank-one updates, but a
+    // quarter of the sequentially dependent stages (the kernel is bound by that latency, not by flops).
+    // A missing entry becomes a virtual unit observation of nothing (zero row, unit pivot).
     T quad = T(0);
+    if constexpr (TM % 4 == 0) {
+      constexpr int NB = 4, RS = D + 4;
 #pragma unroll
-    for (int i0 = 0; i0 < D; i0 += TM) {
-#pragma unroll
-      for (int qq = 0; qq < TM; ++qq) {
-        const int i = i0 + qq;
-        if (i < d && ((obs_mask >> i) & 1u)) {  // warp-uniform
-          T* rb = rowbuf + parity * (D + 4);
+      for (int blk = 0; blk < D / NB; ++blk) {
+        constexpr int dummy = 0; (void)dummy;
+        const int i0 = blk * NB;
+        const unsigned bits = (obs_mask >> i0) & 0xFu;
+        if (bits != 0u) {  // warp-uniform
+          T* rb = rowbuf + parity * (NB * RS);
           parity ^= 1;
           if (ty == i0 / TM) {
-            stv<T, TN>(rb + tx * TN, p[qq]);
-            if (tx == 0) rb[D] = mreg[qq];
+#pragma unroll
+            for (int aa = 0; aa < NB; ++aa) {
+              stv<T, TN>(rb + aa * RS + tx * TN, p[(i0 % TM) + aa]);
+              if (tx == 0) rb[aa * RS + D] = mreg[(i0 % TM) + aa];
+            }
           }
           __syncwarp();
-          const T sv = rb[i] + rdv[i];
-          const T inv = T(1) / sv;
-          const T innov = ev[i] - rb[D];
-          T ra[TM], rc[TN];
-          ldv<T, TM>(ra, rb + ty * TM);
-          ldv<T, TN>(rc, rb + tx * TN);
+          T ok[NB], sr[NB][NB], rdl[NB], evl[NB], RA[NB][TM], RC[NB][TN], v[NB];
+          ldv<T, NB>(rdl, rdv + i0);
+          ldv<T, NB>(evl, ev + i0);
 #pragma unroll
-          for (int r = 0; r < TM; ++r) {
-            const T kr = ra[r] * inv;
-#pragma unroll
-            for (int cc = 0; cc < TN; ++cc) p[r][cc] = fma_(-kr, rc[cc], p[r][cc]);
-            mreg[r] = fma_(kr, innov, mreg[r]);  // only the tx == 0 copies are ever read
+          for (int aa = 0; aa < NB; ++aa) {
+            ok[aa] = ((bits >> aa) & 1u) ? T(1) : T(0);
+            ldv<T, NB>(sr[aa], rb + aa * RS + i0);
+            ldv<T, TM>(RA[aa], rb + aa * RS + ty * TM);
+            ldv<T, TN>(RC[aa], rb + aa * RS + tx * TN);
+            v[aa] = ok[aa] * (evl[aa] - rb[aa * RS + D]);
           }
-          quad = fma_(innov * innov, inv, quad);
-          if (lane == 0) svbuf[i] = sv;
+          // masked S_b: off-diagonals vanish, diagonal becomes 1
+          T L[NB][NB], inv[NB];
+#pragma unroll
+          for (int aa = 0; aa < NB; ++aa)
+#pragma unroll
+            for (int bb = 0; bb <= aa; ++bb)
+              L[aa][bb] = (aa == bb) ? (ok[aa] != T(0) ? sr[aa][aa] + rdl[aa] : T(1)) : ok[aa] * ok[bb] * sr[aa][bb];
+          // 4 x 4 Cholesky in registers
+#pragma unroll
+          for (int k = 0; k < NB; ++k) {
+            T piv = L[k][k];
+#pragma unroll
+            for (int j = 0; j < k; ++j) piv = fma_(-L[k][j], L[k][j], piv);
+            if (lane == 0) svbuf[i0 + k] = piv;   // conditional innovation variance of observation i0 + k
+            T lkk;
+            pivot_<T>(piv, lkk, inv[k]);
+            L[k][k] = lkk;
+#pragma unroll
+            for (int r = k + 1; r < NB; ++r) {
+              T acc = L[r][k];
+#pragma unroll
+              for (int j = 0; j < k; ++j) acc = fma_(-L[r][j], L[k][j], acc);
+              L[r][k] = acc * inv[k];
+            }
+          }
+          // forward substitution on the 4-vectors held by this lane
+          auto fsub = [&](T& x0, T& x1, T& x2, T& x3) {
+            x0 = x0 * inv[0];
+            x1 = fma_(-L[1][0], x0, x1) * inv[1];
+            x2 = fma_(-L[2][1], x1, fma_(-L[2][0], x0, x2)) * inv[2];
+            x3 = fma_(-L[3][2], x2, fma_(-L[3][1], x1, fma_(-L[3][0], x0, x3))) * inv[3];
+          };
+#pragma unroll
+          for (int aa = 0; aa < NB; ++aa) {
+#pragma unroll
+            for (int r = 0; r < TM; ++r) RA[aa][r] *= ok[aa];
+#pragma unroll
+            for (int cc = 0; cc < TN; ++cc) RC[aa][cc] *= ok[aa];
+          }
+#pragma unroll
+          for (int r = 0; r < TM; ++r) fsub(RA[0][r], RA[1][r], RA[2][r], RA[3][r]);
+#pragma unroll
+          for (int cc = 0; cc < TN; ++cc) fsub(RC[0][cc], RC[1][cc], RC[2][cc], RC[3][cc]);
+          fsub(v[0], v[1], v[2], v[3]);
+#pragma unroll
+          for (int aa = 0; aa < NB; ++aa) {
+#pragma unroll
+            for (int r = 0; r < TM; ++r) {
+#pragma unroll
+              for (int cc = 0; cc < TN; ++cc) p[r][cc] = fma_(-RA[aa][r], RC[aa][cc], p[r][cc]);
+              mreg[r] = fma_(RA[aa][r], v[aa], mreg[r]);  // only the tx == 0 copies are ever read
+            }
+            quad = fma_(v[aa], v[aa], quad);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i0 = 0; i0 < D; i0 += TM) {
+#pragma unroll
+        for (int qq = 0; qq < TM; ++qq) {
+          const int i = i0 + qq;
+          if (i < d && ((obs_mask >> i) & 1u)) {  // warp-uniform
+            T* rb = rowbuf + parity * (D + 4);
+            parity ^= 1;
+            if (ty == i0 / TM) {
+              stv<T, TN>(rb + tx * TN, p[qq]);
+              if (tx == 0) rb[D] = mreg[qq];
+            }
+            __syncwarp();
+            const T sv = rb[i] + rdv[i];
+            const T inv = T(1) / sv;
+            const T innov = ev[i] - rb[D];
+            T ra[TM], rc[TN];
+            ldv<T, TM>(ra, rb + ty * TM);
+            ldv<T, TN>(rc, rb + tx * TN);
+#pragma unroll
+            for (int r = 0; r < TM; ++r) {
+              const T kr = ra[r] * inv;
+#pragma unroll
+              for (int cc = 0; cc < TN; ++cc) p[r][cc] = fma_(-kr, rc[cc], p[r][cc]);
+              mreg[r] = fma_(kr, innov, mreg[r]);  // only the tx == 0 copies are ever read
+            }
+            quad = fma_(innov * innov, inv, quad);
+            if (lane == 0) svbuf[i] = sv;
+          }
         }
       }
     }
