@@ -31,7 +31,7 @@ import numpy as np  # noqa: E402
 METRIC = "time-steps x chains / second per Gibbs sweep (aux-Kalman)"
 UNIT = "time-steps*chains/s"
 SV = dict(nu=0.0, phi=0.9, tau=2.0, rho=0.25)
-WORKLOAD = dict(d=30, T=1024, chains_per_gpu=1024, order=2, delta=0.1, dtype="f32")
+WORKLOAD = dict(d=30, T=1024, chains_per_gpu=1024, order=2, delta=0.005, dtype="f32")  # delta ~ 40 % acceptance
 
 
 def make_data(d, T, seed):
@@ -131,7 +131,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(parts)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -168,6 +168,8 @@ def run_gpu(args):
     d, T, C, order, delta = w["d"], w["T"], w["chains_per_gpu"], w["order"], w["delta"]
     if args.chains:
         C = args.chains
+    if args.delta > 0:
+        delta = args.delta
     dtype = torch.float32
     es = 4
     (m0, P0, F, Q, b), xs_true, ys = make_data(d, T, 20250002)
@@ -357,10 +359,11 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU (debug)")
+    ap.add_argument("--delta", type=float, default=0.0, help="override the step size delta (debug)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--dense-r", action="store_true",
                     help="materialise R_t = Omega_t as dense [C,T,d,d] like the reference (default: diagonal)")
