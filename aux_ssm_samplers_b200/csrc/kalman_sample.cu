@@ -220,40 +220,59 @@ __global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) sample_elements_
   }
 }
 
-// pass 2: x_{T-1} = e_{T-1};  x_t = G_t x_{t+1} + e_t.  One CTA of 64 threads per unit, thread i owns x_t[i];
-// G^T is read column-wise (coalesced over i), eight independent loads in flight per thread.
-template <typename T>
+// pass 2: x_{T-1} = e_{T-1};  x_t = G_t x_{t+1} + e_t.  One CTA of 64 threads per unit, thread i owns x_t[i] and
+// column i of G_t^T (coalesced over i).  The whole column of step t-1 is requested into registers before the
+// product of step t is formed, so the strictly sequential loop never waits for DRAM.
+template <typename T, int D>
 __global__ void __launch_bounds__(64) sample_replay_kernel(SampleArgs<T> a) {
   const int ul = blockIdx.x, unit = a.unit0 + ul, dx = a.d.dx, ssz = dx * dx + dx, Tn = a.d.T;
   const int c = unit / a.d.n_batch, b = unit % a.d.n_batch;
-  __shared__ T xb[2][AUXSSM_MAX_DIM];
+  __shared__ __align__(16) T xb[2][D];
   const int i = threadIdx.x;
+  const bool act = i < dx;
   const T* base = a.steps + (int64_t)ul * Tn * ssz;
   T* xo = a.xs + unit_off(a.d.xs, c, b);
+  if (i < D) { xb[0][i] = T(0); xb[1][i] = T(0); }
+  __syncthreads();
   T x = T(0);
-  if (i < dx) {
+  if (act) {
     x = base[(int64_t)(Tn - 1) * ssz + dx * dx + i];
     xb[0][i] = x;
     xo[(int64_t)(Tn - 1) * a.d.xs.time + i] = x;
   }
+  T gn[D], en = T(0);
+#pragma unroll
+  for (int k = 0; k < D; ++k) gn[k] = T(0);
+  auto fetch = [&](int tt) {
+    if (tt >= 0 && act) {
+      const T* g = base + (int64_t)tt * ssz;  // G^T (row k, column i) then e
+#pragma unroll
+      for (int k = 0; k < D; ++k) if (k < dx) gn[k] = g[k * dx + i];
+      en = g[dx * dx + i];
+    }
+  };
+  fetch(Tn - 2);
   __syncthreads();
   int cur = 0;
-  constexpr int PF = 8;
+  constexpr int V = (D >= 4) ? 4 : D;
   for (int t = Tn - 2; t >= 0; --t) {
-    const T* g = base + (int64_t)t * ssz;  // G^T (row k, column i) then e
-    if (i < dx) {
-      T acc0 = g[dx * dx + i], acc1 = T(0);
-      for (int k0 = 0; k0 < dx; k0 += PF) {
-        T gv[PF];
+    T gc[D];
 #pragma unroll
-        for (int q = 0; q < PF; ++q) gv[q] = (k0 + q < dx) ? g[(k0 + q) * dx + i] : T(0);
+    for (int k = 0; k < D; ++k) gc[k] = gn[k];
+    const T ec = en;
+    fetch(t - 1);
+    T acc0 = ec, acc1 = T(0);
 #pragma unroll
-        for (int q = 0; q < PF; ++q) {
-          const T xv = (k0 + q < dx) ? xb[cur][k0 + q] : T(0);
-          if (q & 1) acc1 = fma_(gv[q], xv, acc1); else acc0 = fma_(gv[q], xv, acc0);
-        }
+    for (int k = 0; k < D; k += V) {
+      T xv[V];
+      ldv<T, V>(xv, &xb[cur][k]);
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        if (q & 1) acc1 = fma_(gc[k + q], xv[q], acc1); else acc0 = fma_(gc[k + q], xv[q], acc0);
       }
-      x = acc0 + acc1;
+    }
+    x = acc0 + acc1;
+    if (act) {
       xb[cur ^ 1][i] = x;
       xo[(int64_t)t * a.d.xs.time + i] = x;
     }
@@ -295,7 +314,7 @@ template <typename T, int D> static int launch_sample(cudaStream_t st, SampleArg
     if (lean) sample_elements_kernel<T, D, true><<<dim3(a.n_units, n_tiles), NT, smem, st>>>(a);
     else sample_elements_kernel<T, D, false><<<dim3(a.n_units, n_tiles), NT, smem, st>>>(a);
     AUXSSM_CHECK_LAUNCH("auxssm_kalman_sample (elements)");
-    sample_replay_kernel<T><<<a.n_units, 64, 0, st>>>(a);
+    sample_replay_kernel<T, D><<<a.n_units, 64, 0, st>>>(a);
     AUXSSM_CHECK_LAUNCH("auxssm_kalman_sample (replay)");
   }
   return AUXSSM_OK;
