@@ -617,24 +617,38 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
             }
           }
           __syncwarp();
-          T ok[NB], sr[NB][NB], rdl[NB], evl[NB], RA[NB][TM], RC[NB][TN], v[NB];
+          T sr[NB][NB], rdl[NB], evl[NB], RA[NB][TM], RC[NB][TN], v[NB];
           ldv<T, NB>(rdl, rdv + i0);
           ldv<T, NB>(evl, ev + i0);
 #pragma unroll
           for (int aa = 0; aa < NB; ++aa) {
-            ok[aa] = ((bits >> aa) & 1u) ? T(1) : T(0);
             ldv<T, NB>(sr[aa], rb + aa * RS + i0);
             ldv<T, TM>(RA[aa], rb + aa * RS + ty * TM);
             ldv<T, TN>(RC[aa], rb + aa * RS + tx * TN);
-            v[aa] = ok[aa] * (evl[aa] - rb[aa * RS + D]);
+            v[aa] = evl[aa] - rb[aa * RS + D];
           }
-          // masked S_b: off-diagonals vanish, diagonal becomes 1
           T L[NB][NB], inv[NB];
+          if (bits == 0xFu) {  // all four observed (the common case): S_b = P[I, I] + diag(r_I)
 #pragma unroll
-          for (int aa = 0; aa < NB; ++aa)
+            for (int aa = 0; aa < NB; ++aa)
 #pragma unroll
-            for (int bb = 0; bb <= aa; ++bb)
-              L[aa][bb] = (aa == bb) ? (ok[aa] != T(0) ? sr[aa][aa] + rdl[aa] : T(1)) : ok[aa] * ok[bb] * sr[aa][bb];
+              for (int bb = 0; bb <= aa; ++bb) L[aa][bb] = (aa == bb) ? sr[aa][aa] + rdl[aa] : sr[aa][bb];
+          } else {             // masked S_b: off-diagonals vanish, diagonal becomes 1, rows of P[I, :] are zeroed
+#pragma unroll
+            for (int aa = 0; aa < NB; ++aa) {
+              const T oka = ((bits >> aa) & 1u) ? T(1) : T(0);
+#pragma unroll
+              for (int bb = 0; bb <= aa; ++bb) {
+                const T okb = ((bits >> bb) & 1u) ? T(1) : T(0);
+                L[aa][bb] = (aa == bb) ? (oka != T(0) ? sr[aa][aa] + rdl[aa] : T(1)) : oka * okb * sr[aa][bb];
+              }
+#pragma unroll
+              for (int r = 0; r < TM; ++r) RA[aa][r] *= oka;
+#pragma unroll
+              for (int cc = 0; cc < TN; ++cc) RC[aa][cc] *= oka;
+              v[aa] *= oka;
+            }
+          }
           // 4 x 4 Cholesky in registers
 #pragma unroll
           for (int k = 0; k < NB; ++k) {
@@ -660,13 +674,6 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
             x2 = fma_(-L[2][1], x1, fma_(-L[2][0], x0, x2)) * inv[2];
             x3 = fma_(-L[3][2], x2, fma_(-L[3][1], x1, fma_(-L[3][0], x0, x3))) * inv[3];
           };
-#pragma unroll
-          for (int aa = 0; aa < NB; ++aa) {
-#pragma unroll
-            for (int r = 0; r < TM; ++r) RA[aa][r] *= ok[aa];
-#pragma unroll
-            for (int cc = 0; cc < TN; ++cc) RC[aa][cc] *= ok[aa];
-          }
 #pragma unroll
           for (int r = 0; r < TM; ++r) fsub(RA[0][r], RA[1][r], RA[2][r], RA[3][r]);
 #pragma unroll

@@ -1,0 +1,99 @@
+"""Properties at BASELINE.json's full sizes (where the NumPy oracle would take minutes): the structured fast
+paths must agree with the general dense kernels on identical inputs, and the cSMC outputs must be internally
+consistent (size-independent invariants of the reference algorithm)."""
+import numpy as np
+import numpy.testing as npt
+import pytest
+import torch
+
+from oracle import sv as osv
+
+pytestmark = pytest.mark.gpu
+
+
+def _sv_setup(d, T, C, seed=0):
+    rng = np.random.default_rng(seed)
+    m0, P0, F, Q, b = osv.get_dynamics(0.0, 0.9, 2.0, 0.25, d)
+    xs_true, ys = osv.get_data(rng, 0.0, 0.9, 2.0, 0.25, d, T)
+    to = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device="cuda")
+    x = to(xs_true[None] + 0.3 * rng.standard_normal((C, T, d)))
+    u = x + 0.05 * torch.randn_like(x)
+    return to(ys), to(m0), to(P0), to(F), to(Q), to(b), x, u
+
+
+def test_structured_filter_and_sampler_match_general_kernels_at_full_T():
+    """configs[1] shape (d=30, T=1024): one-warp structured filter (H=I, diagonal R, diagonal F hint) and lean
+    sampler vs the general dense-R / no-hint kernels, same inputs, fp32 tolerance 1e-3."""
+    from aux_ssm_samplers_b200 import kalman, stochastic_volatility as sv
+    d, T, C, delta = 30, 1024, 24, 0.005
+    ys, m0, P0, F, Q, b, x, u = _sv_setup(d, T, C)
+    aux_d, _, Rd, _ = sv.observations_factory(ys, x, u, delta, 2, dense_R=True)
+    aux_s, _, Rs, _ = sv.observations_factory(ys, x, u, delta, 2, dense_R=False)
+    npt.assert_array_equal(aux_d.cpu().numpy(), aux_s.cpu().numpy())
+    Fs, Qs, bs = F.reshape(1, d, d), Q.reshape(1, d, d), b.reshape(1, d)
+    lg_d = kalman.LGSSM(m0, P0, Fs, Qs, bs, None, Rd, None)
+    lg_s = kalman.LGSSM(m0, P0, Fs, Qs, bs, None, Rs, None)
+    ms_d, Ps_d, ell_d = kalman.filtering(aux_d, lg_d, False)
+    ms_s, Ps_s, ell_s = kalman.filtering(aux_s, lg_s, True, f_diagonal=True)
+    ms_c, Ps_c, ell_c = kalman.filtering(aux_s, lg_s, True, f_diagonal=True, time_chunks=8)
+    for a_, b_ in ((ms_s, ms_d), (Ps_s, Ps_d), (ell_s, ell_d), (ms_c, ms_d), (Ps_c, Ps_d), (ell_c, ell_d)):
+        a_, b_ = a_.double().cpu().numpy(), b_.double().cpu().numpy()
+        # absolute floor on the scale of the PREDICTED covariance: P - K S K^T cancels ~2 digits at delta=0.005
+        npt.assert_allclose(a_, b_, rtol=1e-3, atol=1e-4 * max(float(Q.abs().max()), np.abs(b_).max() * 10))
+    assert torch.isfinite(Ps_s).all() and (torch.diagonal(Ps_s, dim1=-2, dim2=-1) > 0).all()
+    npt.assert_array_equal(Ps_s.cpu().numpy(), Ps_s.transpose(-1, -2).cpu().numpy())  # exactly symmetric
+    eps = torch.randn_like(ms_d)
+    xs_g = kalman.sampling(eps, ms_d, Ps_d, lg_d, False)
+    xs_l = kalman.sampling(eps, ms_d, Ps_d, lg_d, True, f_diagonal=True)
+    npt.assert_allclose(xs_l.double().cpu().numpy(), xs_g.double().cpu().numpy(), rtol=1e-3,
+                        atol=1e-2 * float(xs_g.abs().max()))
+    lp_d = kalman.posterior_logpdf(aux_d, xs_g, ell_d, lg_d)
+    lp_s = kalman.posterior_logpdf(aux_s, xs_g, ell_d, lg_s)
+    npt.assert_allclose(lp_s.double().cpu().numpy(), lp_d.double().cpu().numpy(), rtol=1e-3)
+
+
+def test_full_sweep_is_finite_and_moves_at_bench_shape():
+    from aux_ssm_samplers_b200 import stochastic_volatility as sv
+    from aux_ssm_samplers_b200.draws import TorchDraws
+    from aux_ssm_samplers_b200.kalman import KalmanSampler
+    d, T, C = 30, 1024, 64
+    ys, m0, P0, F, Q, b, x, _ = _sv_setup(d, T, C, seed=1)
+    _, kernel = sv.get_kernel(ys, m0, P0, F, Q, b, parallel=True, order=2)
+    state, key = KalmanSampler(x, True), TorchDraws(3)
+    acc = []
+    for _ in range(4):
+        state = kernel(key, state, 0.005)
+        acc.append(float(state.updated.float().mean()))
+    assert torch.isfinite(state.x).all()
+    assert 0.05 < np.mean(acc) <= 1.0, acc
+    assert not torch.equal(state.x, x)
+
+
+@pytest.mark.parametrize("backward", [True, False])
+def test_csmc_invariants_at_config3_shape(backward):
+    """configs[2] shape per chain (N=1024, d=1 SV, T=4096), a few chains: ancestors / history consistency."""
+    from aux_ssm_samplers_b200 import csmc
+    from aux_ssm_samplers_b200.draws import TorchDraws
+    d, N, T, C = 1, 1024, 4096, 3
+    rng = np.random.default_rng(2)
+    m0, P0, F, Q, b = osv.get_dynamics(0.0, 0.9, 2.0, 0.25, d)
+    xs_true, ys = osv.get_data(rng, 0.0, 0.9, 2.0, 0.25, d, T)
+    to = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device="cuda")
+    M0 = csmc.GaussianDistribution(to(m0), to(P0))
+    Mt = csmc.LinearGaussianDynamics(to(F), to(Q), to(b))
+    G = csmc.StochasticVolatilityPotential(to(ys))
+    _, kernel = csmc.get_kernel(M0, G, Mt, G, N, backward, return_history=True)
+    x_star = to(xs_true[None] + 0.1 * rng.standard_normal((C, T, d)))
+    st, h = kernel(TorchDraws(5), csmc.CSMCState(x_star, None))
+    B, As, xs, lws = h["ancestors"].long(), h["As"].long(), h["xs"], h["log_ws"]
+    assert (As[..., 0] == 0).all() and (As >= 0).all() and (As < N).all()      # resamplings.py:36
+    npt.assert_array_equal(xs[:, :, 0].cpu().numpy(), x_star.cpu().numpy())     # csmc.py:76,92
+    assert (B >= 0).all() and (B < N).all()
+    picked = torch.gather(xs, 2, B[:, :, None, None].expand(C, T, 1, d))[:, :, 0]
+    npt.assert_array_equal(st.x.cpu().numpy(), picked.cpu().numpy())             # x_t = xs[t, B_t]
+    npt.assert_array_equal(st.updated.cpu().numpy(), (B != 0).cpu().numpy())     # csmc.py:59
+    assert torch.isfinite(lws).all() and torch.isfinite(st.x).all()
+    if not backward:  # ancestor tracing: B_{t-1} = A_t[B_t]  (csmc.py:116-121)
+        npt.assert_array_equal(B[:, :-1].cpu().numpy(), torch.gather(As, 2, B[:, 1:, None])[:, :, 0].cpu().numpy())
+    if backward:  # backward sampling rejuvenates the whole path; ancestor tracing degenerates by design
+        assert float(st.updated.float().mean()) > 0.5
