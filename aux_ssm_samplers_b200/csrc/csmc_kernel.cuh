@@ -199,9 +199,8 @@ template <typename T, int D> __device__ __forceinline__ T potential(const auxssm
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       if (i < dsc.d) {
-        const T sc = exp(T(0.5) * x[i]);
-        const T z = y[i] / sc;
-        acc += T(-0.5) * z * z - log(sc) - log_2pi_half<T>();
+        // log N(y; 0, exp(x / 2)) = -y^2 exp(-x) / 2 - x / 2 - log(2 pi) / 2: one exp, no log / divide
+        acc += T(-0.5) * y[i] * y[i] * exp(-x[i]) - T(0.5) * x[i] - log_2pi_half<T>();
       }
     }
   }

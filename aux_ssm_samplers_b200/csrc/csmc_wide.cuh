@@ -40,11 +40,21 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // compact global [rows][d] -> padded shared [rows][LD], element-wise asynchronous copies.
 // magic = 2^32 / d + 1 gives e / d exactly for e < 2^13, d <= 32.
+// Even d: two elements per copy (rows then start on 2-element boundaries on both sides).
 template <typename T, int LD>
 __device__ __forceinline__ void stage_rows_async(T* dst, const T* src, int total, int d, unsigned magic) {
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    const int n = (int)__umulhi((unsigned)e, magic), k = e - n * d;
-    cp_async<sizeof(T)>(dst + n * LD + k, src + e);
+  if ((d & 1) == 0) {
+#pragma unroll 2
+    for (int e = 2 * threadIdx.x; e < total; e += 2 * blockDim.x) {
+      const int n = (int)__umulhi((unsigned)e, magic), k = e - n * d;
+      cp_async<2 * sizeof(T)>(dst + n * LD + k, src + e);
+    }
+  } else {
+#pragma unroll 2
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int n = (int)__umulhi((unsigned)e, magic), k = e - n * d;
+      cp_async<sizeof(T)>(dst + n * LD + k, src + e);
+    }
   }
 }
 
@@ -83,41 +93,63 @@ template <typename T, int D, int LD> __device__ __forceinline__ void tri_inverse
   }
 }
 
-// -0.5 |L^{-1} r|^2 by one thread (r overwritten)
-template <typename T, int D, int LD> __device__ __forceinline__ T quad_form_ld(const T* L, const T* invd, T (&r)[D]) {
-  T q2 = T(0);
+// -0.5 |L^{-1} r|^2 by one full warp: lane l owns row l (its entry of r and row l of L in registers) and the
+// columns are swept left to right, the finished entry z_k travelling by shuffle.  Every lane gets the result.
+template <typename T, int D, int LD>
+__device__ __forceinline__ T warp_quad_form(const T* L, const T* invd, T r_lane, int lane) {
+  constexpr int V = WideCfg<T, D>::V;
+  const int row = lane < D ? lane : 0;
+  T lrow[D];
 #pragma unroll
-  for (int i = 0; i < D; ++i) {
-    T a0 = r[i], a1 = T(0);
+  for (int k = 0; k < D; k += V) {
+    T l[V];
+    ldv<T, V>(l, L + row * LD + k);
 #pragma unroll
-    for (int k = 0; k < i; ++k) {
-      if (k & 1) a1 = fma_(-L[i * LD + k], r[k], a1); else a0 = fma_(-L[i * LD + k], r[k], a0);
-    }
-    r[i] = (a0 + a1) * invd[i];
-    q2 = fma_(r[i], r[i], q2);
+    for (int q = 0; q < V; ++q) lrow[k + q] = l[q];
+  }
+  const T inv = lane < D ? invd[row] : T(0);
+  T r = lane < D ? r_lane : T(0), q2 = T(0);
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const T zk = __shfl_sync(0xffffffffu, r * inv, k);
+    if (lane > k) r = fma_(-lrow[k], zk, r);
+    q2 = fma_(zk, zk, q2);
   }
   return T(-0.5) * q2;
 }
 
-// acc[j][c] += sum_k x(r0 + 32 j, k) * M[c0 + c][k]; `xf(xv, row, k)` produces V operands of row `row`
+// acc[j][c] += sum_k x(r0 + 32 j, k) * M[c0 + c][k]; `xf(xv, row, k)` produces V operands of row `row`.
+// Register double buffering: the operands of k-block kb + 1 are requested before the FMAs of block kb issue
+// (two warps per scheduler cannot hide the shared-memory latency on their own).  Two blocks per trip keep the
+// buffer indices static and the sweep inside the instruction cache.
 template <typename T, int D, int TM, class XF>
 __device__ __forceinline__ void wide_mm(const T* M, int r0, int c0, T (&acc)[TM][4], XF xf) {
-  constexpr int V = WideCfg<T, D>::V, LD = WideCfg<T, D>::LD;
+  constexpr int V = WideCfg<T, D>::V, LD = WideCfg<T, D>::LD, NKB = D / V;
+  static_assert(NKB % 2 == 0, "even number of k-blocks expected");
+  T mv[2][4][V], xv[2][TM][V];
+  auto load = [&](int b, int k) {
 #pragma unroll
-  for (int k = 0; k < D; k += V) {
-    T mv[4][V];
+    for (int c = 0; c < 4; ++c) ldv<T, V>(mv[b][c], M + (c0 + c) * LD + k);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) ldv<T, V>(mv[c], M + (c0 + c) * LD + k);
+    for (int j = 0; j < TM; ++j) xf(xv[b][j], r0 + 32 * j, k);
+  };
+  auto mac = [&](int b) {
 #pragma unroll
     for (int j = 0; j < TM; ++j) {
-      T xv[V];
-      xf(xv, r0 + 32 * j, k);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
-        for (int q = 0; q < V; ++q) acc[j][c] = fma_(xv[q], mv[c][q], acc[j][c]);
+        for (int q = 0; q < V; ++q) acc[j][c] = fma_(xv[b][j][q], mv[b][c][q], acc[j][c]);
       }
     }
+  };
+  load(0, 0);
+#pragma unroll 1
+  for (int kb = 0; kb < NKB; kb += 2) {
+    load(1, (kb + 1) * V);
+    mac(0);
+    if (kb + 2 < NKB) load(0, (kb + 2) * V);
+    mac(1);
   }
 }
 
@@ -387,12 +419,8 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
       // (4) prior residuals  z = (xn - xpred) W^T, history
       T pin = T(0);
       if (PROP != AUXSSM_PROP_BOOTSTRAP) {
-        if (PROP == AUXSSM_PROP_GUIDED && i == 0) {
-          T r[D];
-#pragma unroll
-          for (int k = 0; k < D; ++k) r[k] = vxs[k] - vmu0[k];
-          pin = quad_form_ld<T, D, LD>(mcL, invl, r);
-        }
+        if (PROP == AUXSSM_PROP_GUIDED && warp == 0)
+          pin = warp_quad_form<T, D, LD>(mcL, invl, lane < D ? vxs[lane] - vmu0[lane] : T(0), lane);
         T acc[TM][4];
 #pragma unroll
         for (int j = 0; j < TM; ++j)
@@ -417,9 +445,20 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
       }
       {
         T* xg = xs_h + (int64_t)t * N * d;
-        for (int e = i; e < N * d; e += NT) {
-          const int n = (int)__umulhi((unsigned)e, magic), k = e - n * d;
-          xg[e] = xnb[n * LD + k];
+        if ((d & 1) == 0) {
+#pragma unroll 2
+          for (int e = 2 * i; e < N * d; e += 2 * NT) {
+            const int n = (int)__umulhi((unsigned)e, magic), k = e - n * d;
+            T v[2];
+            ldv<T, 2>(v, xnb + n * LD + k);
+            stv<T, 2>(xg + e, v);
+          }
+        } else {
+#pragma unroll 2
+          for (int e = i; e < N * d; e += NT) {
+            const int n = (int)__umulhi((unsigned)e, magic), k = e - n * d;
+            xg[e] = xnb[n * LD + k];
+          }
         }
       }
       __syncthreads();
@@ -428,25 +467,47 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
       // (5) weights
       T lw = T(0);
       if (active) {
-        T xn[D];
-#pragma unroll
+        // potential and isotropic terms in one rolled pass over the particle's row (padded entries are zero
+        // in every operand and contribute exactly zero)
+        T pot = T(0), su = T(0), sm = T(0);
+        const T inv_s = T(1) / s_c, inv_sig = T(1) / T(dsc.sig);
+#pragma unroll 1
         for (int k = 0; k < D; k += V) {
-          T v[V];
-          ldv<T, V>(v, xnb + i * LD + k);
+          T x[V], y[V], uu[V], mm[V];
+          ldv<T, V>(x, xnb + i * LD + k);
+          ldv<T, V>(y, vy + k);
+          if (PROP != AUXSSM_PROP_BOOTSTRAP) ldv<T, V>(uu, vu + k);
+          if (PROP == AUXSSM_PROP_INDEPENDENT) ldv<T, V>(mm, vmean + k);
 #pragma unroll
-          for (int q = 0; q < V; ++q) xn[k + q] = v[q];
+          for (int q = 0; q < V; ++q) {
+            if (dsc.potential == AUXSSM_POT_SV) {
+              pot = fma_(T(-0.5) * y[q] * y[q], exp(-x[q]), pot) - T(0.5) * x[q];
+            } else if (dsc.potential == AUXSSM_POT_GAUSSIAN) {
+              const T z = (y[q] - x[q]) * inv_sig;
+              pot = fma_(T(-0.5) * z, z, pot);
+            }
+            if (PROP != AUXSSM_PROP_BOOTSTRAP) {
+              const T zu = (x[q] - uu[q]) * inv_s;
+              su = fma_(zu, zu, su);
+            }
+            if (PROP == AUXSSM_PROP_INDEPENDENT) {
+              const T zm = (x[q] - mm[q]) * inv_s;
+              sm = fma_(zm, zm, sm);
+            }
+          }
         }
-        lw = potential<T, D>(dsc, vy, xn);
+        if (dsc.potential == AUXSSM_POT_SV) pot -= T(d) * log_2pi_half<T>();
+        if (dsc.potential == AUXSSM_POT_GAUSSIAN) pot -= T(d) * (log(T(dsc.sig)) + log_2pi_half<T>());
+        lw = pot;
         if (PROP != AUXSSM_PROP_BOOTSTRAP) {
           T q2 = T(0);
 #pragma unroll
           for (int ct = 0; ct < CT; ++ct) q2 += zq[ct * NPAD + i];
           lw += T(-0.5) * q2 + (first ? cst_p0 : cst_q);
         }
-        if (PROP == AUXSSM_PROP_INDEPENDENT && dsc.gradient)
-          lw += iso_logpdf<T, D>(xn, vu, s_c, d) - iso_logpdf<T, D>(xn, vmean, s_c, d);
+        if (PROP == AUXSSM_PROP_INDEPENDENT && dsc.gradient) lw += T(-0.5) * (su - sm);
         if (PROP == AUXSSM_PROP_GUIDED) {
-          lw += iso_logpdf<T, D>(xn, vu, s_c, d);
+          lw += T(-0.5) * su - T(d) * (log(s_c) + log_2pi_half<T>());
           lw -= ((i == 0) ? pin : T(-0.5) * qe) + cst_l;
         }
         lw_h[(int64_t)t * N + i] = lw;
