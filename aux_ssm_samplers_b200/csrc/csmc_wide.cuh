@@ -27,7 +27,9 @@ template <typename T, int D> struct WideCfg {
   static constexpr int V = 16 / sizeof(T);  // elements per 16-byte vector
   static constexpr int LD = D + V;          // row stride of every shared matrix
   static constexpr int NT = 256, NW = NT / 32;
-  static constexpr int CT = D / 4;          // column tiles (4 outputs each), one per warp
+  static constexpr int TN = (D >= 32) ? 8 : 4;  // output columns per warp (register tile TM x TN): every
+                                                // lane-strided particle vector read feeds TN * V FMAs
+  static constexpr int CT = D / TN;         // column tiles, one per warp
   static constexpr int PG = NW / CT;        // warps sharing a column tile split the particle rows
   static_assert(CT >= 1 && CT <= NW && NW % CT == 0, "unsupported D");
 };
@@ -123,13 +125,13 @@ __device__ __forceinline__ T warp_quad_form(const T* L, const T* invd, T r_lane,
 // (two warps per scheduler cannot hide the shared-memory latency on their own).  Two blocks per trip keep the
 // buffer indices static and the sweep inside the instruction cache.
 template <typename T, int D, int TM, class XF>
-__device__ __forceinline__ void wide_mm(const T* M, int r0, int c0, T (&acc)[TM][4], XF xf) {
-  constexpr int V = WideCfg<T, D>::V, LD = WideCfg<T, D>::LD, NKB = D / V;
+__device__ __forceinline__ void wide_mm(const T* M, int r0, int c0, T (&acc)[TM][WideCfg<T, D>::TN], XF xf) {
+  constexpr int V = WideCfg<T, D>::V, LD = WideCfg<T, D>::LD, NKB = D / V, TN = WideCfg<T, D>::TN;
   static_assert(NKB % 2 == 0, "even number of k-blocks expected");
-  T mv[2][4][V], xv[2][TM][V];
+  T mv[2][TN][V], xv[2][TM][V];
   auto load = [&](int b, int k) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) ldv<T, V>(mv[b][c], M + (c0 + c) * LD + k);
+    for (int c = 0; c < TN; ++c) ldv<T, V>(mv[b][c], M + (c0 + c) * LD + k);
 #pragma unroll
     for (int j = 0; j < TM; ++j) xf(xv[b][j], r0 + 32 * j, k);
   };
@@ -137,7 +139,7 @@ __device__ __forceinline__ void wide_mm(const T* M, int r0, int c0, T (&acc)[TM]
 #pragma unroll
     for (int j = 0; j < TM; ++j) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < TN; ++c) {
 #pragma unroll
         for (int q = 0; q < V; ++q) acc[j][c] = fma_(xv[b][j][q], mv[b][c][q], acc[j][c]);
       }
@@ -155,19 +157,20 @@ __device__ __forceinline__ void wide_mm(const T* M, int r0, int c0, T (&acc)[TM]
 
 template <typename T, int D> __host__ __device__ inline size_t csmc_wide_smem_elems(int NPAD) {
   constexpr int LD = WideCfg<T, D>::LD, CT = WideCfg<T, D>::CT;
-  return (size_t)3 * NPAD * LD + (size_t)6 * D * LD + 16 * D + (size_t)CT * NPAD + NPAD + 128 + 32;
+  return (size_t)4 * NPAD * LD + (size_t)6 * D * LD + 16 * D + (size_t)CT * NPAD + NPAD + 128 + 32;
 }
 
 template <typename T, int D, int PROP, int NPAD>
 __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
   using Cfg = WideCfg<T, D>;
-  constexpr int V = Cfg::V, LD = Cfg::LD, NT = Cfg::NT, CT = Cfg::CT, PG = Cfg::PG, TM = NPAD / (32 * PG);
+  constexpr int V = Cfg::V, LD = Cfg::LD, NT = Cfg::NT, CT = Cfg::CT, PG = Cfg::PG, TM = NPAD / (32 * PG),
+                TN = Cfg::TN;
   static_assert(TM >= 1 && NPAD <= NT && NPAD % (32 * PG) == 0, "unsupported NPAD");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const auxssm_csmc_desc& dsc = a.d;
   const int N = dsc.N, d = dsc.d, Tn = dsc.T, i = threadIdx.x;
   const int lane = i & 31, warp = i >> 5;
-  const int c0 = 4 * (warp % CT), r0 = (warp / CT) * (32 * TM) + lane;  // this thread's tile of every product
+  const int c0 = TN * (warp % CT), r0 = (warp / CT) * (32 * TM) + lane;  // this thread's tile of every product
   const bool active = i < N;
   const unsigned magic = 0xffffffffu / (unsigned)d + 1u;
   T* p = reinterpret_cast<T*>(smem_raw);
@@ -178,6 +181,7 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
   T* bufA = p; p += NPAD * LD;
   T* bufB = p; p += NPAD * LD;
   T* bufE = p; p += NPAD * LD;
+  T* bufR = p; p += NPAD * LD;  // xn - xpred, the operand of the prior-density product
   T* mF = p; p += D * LD;
   T* mW = p; p += D * LD;    // chol(Q)^{-1}
   T* mW0 = p; p += D * LD;   // chol(P0)^{-1}
@@ -318,20 +322,20 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
           }
         }
         __syncthreads();
-        T acc[TM][4];
+        T acc[TM][TN];
 #pragma unroll
         for (int j = 0; j < TM; ++j)
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) acc[j][cc] = T(0);
+          for (int cc = 0; cc < TN; ++cc) acc[j][cc] = T(0);
         wide_mm<T, D, TM>(mF, r0, c0, acc, plain(other));
-        T bv[4];
-        ldv<T, 4>(bv, vb + c0);
+        T bv[TN];
+        ldv<T, TN>(bv, vb + c0);
 #pragma unroll
         for (int j = 0; j < TM; ++j) {
-          T o[4];
+          T o[TN];
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) o[cc] = acc[j][cc] + bv[cc];
-          stv<T, 4>(part + (r0 + 32 * j) * LD + c0, o);
+          for (int cc = 0; cc < TN; ++cc) o[cc] = acc[j][cc] + bv[cc];
+          stv<T, TN>(part + (r0 + 32 * j) * LD + c0, o);
         }
         xpb = part; xnb = other;
       }
@@ -367,20 +371,25 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
         if (active) {
 #pragma unroll
           for (int k = 0; k < D; k += V) {
-            T e[V], mu[V], o[V];
+            T e[V], mu[V], o[V], xa[V], r[V];
             ldv<T, V>(e, bufE + i * LD + k);
             ldv<T, V>(mu, (i == 0) ? vxs + k : vmean + k);
+            ldv<T, V>(xa, xpb + i * LD + k);
 #pragma unroll
-            for (int q = 0; q < V; ++q) o[q] = (i == 0) ? mu[q] : fma_(s_c, e[q], mu[q]);
+            for (int q = 0; q < V; ++q) {
+              o[q] = (i == 0) ? mu[q] : fma_(s_c, e[q], mu[q]);
+              r[q] = o[q] - xa[q];
+            }
             stv<T, V>(xnb + i * LD + k, o);
+            stv<T, V>(bufR + i * LD + k, r);
           }
         }
       } else {
-        T acc[TM][4];
+        T acc[TM][TN];
 #pragma unroll
         for (int j = 0; j < TM; ++j)
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) acc[j][cc] = T(0);
+          for (int cc = 0; cc < TN; ++cc) acc[j][cc] = T(0);
         if (PROP == AUXSSM_PROP_GUIDED) {
           const T* X = xpb;
           const T* uu = vu;
@@ -392,11 +401,11 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
             for (int q = 0; q < V; ++q) xv[q] = ub[q] - xa[q];
           });
           if (r0 == 0) {  // mean of the pinned particle's proposal, for its explicit density
-            T xa[4], o[4];
-            ldv<T, 4>(xa, xpb + c0);
+            T xa[TN], o[TN];
+            ldv<T, TN>(xa, xpb + c0);
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) o[cc] = xa[cc] + acc[0][cc];
-            stv<T, 4>(vmu0 + c0, o);
+            for (int cc = 0; cc < TN; ++cc) o[cc] = xa[cc] + acc[0][cc];
+            stv<T, TN>(vmu0 + c0, o);
           }
           wide_mm<T, D, TM>(mcL, r0, c0, acc, plain(bufE));
         } else {
@@ -405,11 +414,20 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
 #pragma unroll
         for (int j = 0; j < TM; ++j) {
           const int row = r0 + 32 * j;
-          T xa[4], o[4];
-          ldv<T, 4>(xa, ((row == 0) ? vxs : xpb + row * LD) + c0);
+          T xa[TN], o[TN];
+          ldv<T, TN>(xa, xpb + row * LD + c0);
+          if (row == 0) {
+            ldv<T, TN>(o, vxs + c0);
+          } else {
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) o[cc] = (row == 0) ? xa[cc] : xa[cc] + acc[j][cc];
-          stv<T, 4>(xnb + row * LD + c0, o);
+            for (int cc = 0; cc < TN; ++cc) o[cc] = xa[cc] + acc[j][cc];
+          }
+          stv<T, TN>(xnb + row * LD + c0, o);
+          if (PROP == AUXSSM_PROP_GUIDED) {
+#pragma unroll
+            for (int cc = 0; cc < TN; ++cc) xa[cc] = o[cc] - xa[cc];
+            stv<T, TN>(bufR + row * LD + c0, xa);
+          }
         }
       }
       __syncthreads();
@@ -421,25 +439,17 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
       if (PROP != AUXSSM_PROP_BOOTSTRAP) {
         if (PROP == AUXSSM_PROP_GUIDED && warp == 0)
           pin = warp_quad_form<T, D, LD>(mcL, invl, lane < D ? vxs[lane] - vmu0[lane] : T(0), lane);
-        T acc[TM][4];
+        T acc[TM][TN];
 #pragma unroll
         for (int j = 0; j < TM; ++j)
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) acc[j][cc] = T(0);
-        const T* Xn = xnb;
-        const T* Xp = xpb;
-        wide_mm<T, D, TM>(first ? mW0 : mW, r0, c0, acc, [Xn, Xp](T (&xv)[V], int row, int k) {
-          T xa[V], xb[V];
-          ldv<T, V>(xa, Xn + row * LD + k);
-          ldv<T, V>(xb, Xp + row * LD + k);
-#pragma unroll
-          for (int q = 0; q < V; ++q) xv[q] = xa[q] - xb[q];
-        });
+          for (int cc = 0; cc < TN; ++cc) acc[j][cc] = T(0);
+        wide_mm<T, D, TM>(first ? mW0 : mW, r0, c0, acc, plain(bufR));
 #pragma unroll
         for (int j = 0; j < TM; ++j) {
           T q2 = T(0);
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) q2 = fma_(acc[j][cc], acc[j][cc], q2);
+          for (int cc = 0; cc < TN; ++cc) q2 = fma_(acc[j][cc], acc[j][cc], q2);
           zq[(warp % CT) * NPAD + r0 + 32 * j] = q2;
         }
       }
@@ -557,10 +567,10 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
         __syncthreads();  // X_t staged; everyone is done with `nxt`
         if (t > 0) stage_rows_async<T, LD>(nxt, xs_h + (int64_t)(t - 1) * N * d, N * d, d, magic);
         // v0 = W (x_sel - b) for this warp's four columns: lane = (k-slice, column), butterfly over slices
-        T v0[4];
+        T v0[TN];
         {
-          constexpr int KS = D / 8;  // k's per lane
-          const int cc = lane & 3, kq = lane >> 2;
+          constexpr int NS = 32 / TN, KS = D / NS;  // k-slices per warp, k's per lane
+          const int cc = lane % TN, kq = lane / TN;
           T pv = T(0);
 #pragma unroll
           for (int q = 0; q < KS; ++q) {
@@ -568,21 +578,21 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
             pv = fma_(mW[(c0 + cc) * LD + k], vsel[k] - vb[k], pv);
           }
 #pragma unroll
-          for (int off = 4; off < 32; off <<= 1) pv += __shfl_xor_sync(0xffffffffu, pv, off);
+          for (int off = TN; off < 32; off <<= 1) pv += __shfl_xor_sync(0xffffffffu, pv, off);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) v0[q] = __shfl_sync(0xffffffffu, pv, q);
+          for (int q = 0; q < TN; ++q) v0[q] = __shfl_sync(0xffffffffu, pv, q);
         }
-        T acc[TM][4];
+        T acc[TM][TN];
 #pragma unroll
         for (int j = 0; j < TM; ++j)
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) acc[j][cc] = T(0);
+          for (int cc = 0; cc < TN; ++cc) acc[j][cc] = T(0);
         wide_mm<T, D, TM>(mWF, r0, c0, acc, plain(cur));
 #pragma unroll
         for (int j = 0; j < TM; ++j) {
           T q2 = T(0);
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
+          for (int cc = 0; cc < TN; ++cc) {
             const T z = v0[cc] - acc[j][cc];
             q2 = fma_(z, z, q2);
           }
