@@ -89,13 +89,20 @@ __device__ __forceinline__ void bwd_solve(const T* L, T* B, const T* dg, int n, 
           const T zi = z[i] * dginv[i];
           z[i] = zi;
           B[i * LD + j] = zi;
+          const T nzi = -zi;
 #pragma unroll
           for (int k = 0; k < ((i + V - 1) / V) * V; k += V) {
             T l[V];
             ldv<T, V>(l, L + i * LD + k);
 #pragma unroll
-            for (int q = 0; q < V; ++q)
-              if (k + q < i) z[k + q] = fma_(-l[q], zi, z[k + q]);
+            for (int q = 0; q < V; q += 2) {
+              if (q + 1 < V && k + q + 1 < i) {  // packed pair (two FMAs per issue slot, see smem_linalg.cuh)
+                const Pair<T> r2 = pair_fma_s(nzi, pair_make(l[q], l[q + 1]), pair_make(z[k + q], z[k + q + 1]));
+                pair_get(r2, z[k + q], z[k + q + 1]);
+              } else if (k + q < i) {
+                z[k + q] = fma_(nzi, l[q], z[k + q]);
+              }
+            }
           }
         }
       }

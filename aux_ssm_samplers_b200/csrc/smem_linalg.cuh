@@ -56,6 +56,39 @@ template <> __device__ __forceinline__ double fma_<double>(double a, double b, d
 
 template <typename T> __device__ __forceinline__ bool finite_(T x) { return isfinite(x); }
 
+// Packed pairs.  fp32: one aligned 64-bit register pair driven by FFMA2 (fma.rn.f32x2, sm_100a), two FMAs per
+// issue slot.  The arithmetic rate is the same as scalar FFMA (measured: profiles/micro/ffma2_probe.cu), but
+// the kernels here are issue-bound, so halving the FMA instruction count frees slots for the loads and
+// shuffles around them.  Each half is an ordinary round-to-nearest fp32 FMA: results are bit-identical to the
+// scalar form.  fp64 keeps two scalar DFMAs behind the same interface.
+template <typename T> struct Pair;
+template <> struct Pair<float> { unsigned long long v; };
+template <> struct Pair<double> { double lo, hi; };
+
+__device__ __forceinline__ Pair<float> pair_make(float a, float b) {
+  Pair<float> p;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(p.v) : "f"(a), "f"(b));
+  return p;
+}
+__device__ __forceinline__ Pair<double> pair_make(double a, double b) { return Pair<double>{a, b}; }
+__device__ __forceinline__ void pair_get(Pair<float> p, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v));
+}
+__device__ __forceinline__ void pair_get(Pair<double> p, double& a, double& b) { a = p.lo; b = p.hi; }
+// a * b + c, element-wise
+__device__ __forceinline__ Pair<float> pair_fma(Pair<float> a, Pair<float> b, Pair<float> c) {
+  Pair<float> r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ Pair<double> pair_fma(Pair<double> a, Pair<double> b, Pair<double> c) {
+  return Pair<double>{fma(a.lo, b.lo, c.lo), fma(a.hi, b.hi, c.hi)};
+}
+// s * b + c with the scalar s applied to both halves (FFMA2 takes it as a broadcast operand, no extra move)
+template <typename T> __device__ __forceinline__ Pair<T> pair_fma_s(T s, Pair<T> b, Pair<T> c) {
+  return pair_fma(pair_make(s, s), b, c);
+}
+
 // MODE 0: C = X^T Y ; MODE 1: C = E + X^T Y ; MODE 2: C = E - X^T Y.   K = inner extent.
 // X, Y, C, E are D x LD shared buffers; C may alias E but must not alias X or Y.
 template <typename T, int D, int MODE>
@@ -67,21 +100,47 @@ __device__ __forceinline__ void mm_tn(const T* __restrict__ X, const T* __restri
   for (int tile = threadIdx.x; tile < TILES; tile += NT) {
     const int ty = tile / TX, tx = tile % TX;
     T acc[TM][TN];
-#pragma unroll
-    for (int r = 0; r < TM; ++r)
-#pragma unroll
-      for (int c = 0; c < TN; ++c) acc[r][c] = T(0);
     const T* xp = X + ty * TM;
     const T* yp = Y + tx * TN;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-      T xa[TM], yb[TN];
-      ldv<T, TM>(xa, xp + k * LD);
-      ldv<T, TN>(yb, yp + k * LD);
+    if constexpr (TN % 2 == 0) {
+      // accumulators as column pairs: one packed FMA per (row, column pair)
+      Pair<T> acc2[TM][TN / 2];
 #pragma unroll
       for (int r = 0; r < TM; ++r)
 #pragma unroll
-        for (int c = 0; c < TN; ++c) acc[r][c] = fma_(xa[r], yb[c], acc[r][c]);
+        for (int c = 0; c < TN / 2; ++c) acc2[r][c] = pair_make(T(0), T(0));
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) {
+        T xa[TM], yb[TN];
+        ldv<T, TM>(xa, xp + k * LD);
+        ldv<T, TN>(yb, yp + k * LD);
+        Pair<T> yb2[TN / 2];
+#pragma unroll
+        for (int c = 0; c < TN / 2; ++c) yb2[c] = pair_make(yb[2 * c], yb[2 * c + 1]);
+#pragma unroll
+        for (int r = 0; r < TM; ++r)
+#pragma unroll
+          for (int c = 0; c < TN / 2; ++c) acc2[r][c] = pair_fma_s(xa[r], yb2[c], acc2[r][c]);
+      }
+#pragma unroll
+      for (int r = 0; r < TM; ++r)
+#pragma unroll
+        for (int c = 0; c < TN / 2; ++c) pair_get(acc2[r][c], acc[r][2 * c], acc[r][2 * c + 1]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < TM; ++r)
+#pragma unroll
+        for (int c = 0; c < TN; ++c) acc[r][c] = T(0);
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) {
+        T xa[TM], yb[TN];
+        ldv<T, TM>(xa, xp + k * LD);
+        ldv<T, TN>(yb, yp + k * LD);
+#pragma unroll
+        for (int r = 0; r < TM; ++r)
+#pragma unroll
+          for (int c = 0; c < TN; ++c) acc[r][c] = fma_(xa[r], yb[c], acc[r][c]);
+      }
     }
 #pragma unroll
     for (int r = 0; r < TM; ++r) {
@@ -287,13 +346,21 @@ __device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n
           if (dginv) dginv[k] = inv;
         }
         __syncwarp();
+        const T nlik = -lik;
 #pragma unroll
         for (int j = ((k + 1) / V) * V; j < D; j += V) {
           T c[V];
           ldv<T, V>(c, cb + j);
 #pragma unroll
-          for (int q = 0; q < V; ++q)
-            if (j + q > k) row[j + q] = fma_(-lik, c[q], row[j + q]);
+          for (int q = 0; q < V; q += 2) {
+            if (q + 1 < V && j + q > k) {  // both columns of the pair are still open: one packed FMA
+              const Pair<T> r2 = pair_fma_s(nlik, pair_make(c[q], c[q + 1]), pair_make(row[j + q], row[j + q + 1]));
+              pair_get(r2, row[j + q], row[j + q + 1]);
+            } else {
+              if (j + q > k) row[j + q] = fma_(nlik, c[q], row[j + q]);
+              if (q + 1 < V && j + q + 1 > k) row[j + q + 1] = fma_(nlik, c[q + 1], row[j + q + 1]);
+            }
+          }
         }
       }
     }
@@ -336,21 +403,26 @@ __device__ __forceinline__ void fwd_solve_reg(const T* L, T* B, T* bvec, const T
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       if (PADDED || i < n) {
-        T acc0 = is_vec ? bvec[i] : B[i * LD + j];
-        T acc1 = T(0);
+        // dot product L[i, :i] . z[:i] in two interleaved partial sums (even / odd k), packed pairwise
+        const T rhs = is_vec ? bvec[i] : B[i * LD + j];
+        Pair<T> s2 = pair_make(T(0), T(0));
+        T tail = T(0);
 #pragma unroll
         for (int k = 0; k < ((i + V - 1) / V) * V; k += V) {
           T l[V];
           ldv<T, V>(l, L + i * LD + k);
 #pragma unroll
-          for (int q = 0; q < V; ++q) {
-            if (k + q < i) {
-              if ((q & 1) == 0) acc0 = fma_(-l[q], z[k + q], acc0);
-              else acc1 = fma_(-l[q], z[k + q], acc1);
+          for (int q = 0; q < V; q += 2) {
+            if (q + 1 < V && k + q + 1 < i) {
+              s2 = pair_fma(pair_make(l[q], l[q + 1]), pair_make(z[k + q], z[k + q + 1]), s2);
+            } else if (k + q < i) {
+              tail = fma_(l[q], z[k + q], tail);
             }
           }
         }
-        z[i] = (acc0 + acc1) * dginv[i];
+        T s_even, s_odd;
+        pair_get(s2, s_even, s_odd);
+        z[i] = (rhs - ((s_even + tail) + s_odd)) * dginv[i];
         if (is_vec) bvec[i] = z[i]; else B[i * LD + j] = z[i];
       }
     }
