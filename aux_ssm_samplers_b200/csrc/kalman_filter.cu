@@ -586,8 +586,18 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
     if (t > 0) {
 #pragma unroll
       for (int r = 0; r < TM; ++r) {
+        if constexpr (TN % 2 == 0) {
 #pragma unroll
-        for (int cc = 0; cc < TN; ++cc) p[r][cc] = fma_(fa[r] * fc[cc], p[r][cc], q[r][cc]);
+          for (int c2 = 0; c2 < TN / 2; ++c2) {  // packed pairs: two FMAs per issue slot (smem_linalg.cuh)
+            const Pair<T> ff = pair_mul_s(fa[r], pair_make(fc[2 * c2], fc[2 * c2 + 1]));
+            const Pair<T> pp = pair_fma(ff, pair_make(p[r][2 * c2], p[r][2 * c2 + 1]),
+                                        pair_make(q[r][2 * c2], q[r][2 * c2 + 1]));
+            pair_get(pp, p[r][2 * c2], p[r][2 * c2 + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < TN; ++cc) p[r][cc] = fma_(fa[r] * fc[cc], p[r][cc], q[r][cc]);
+        }
         mreg[r] = fma_(fa[r], mreg[r], ba[r]);
       }
     }
@@ -668,24 +678,57 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
             }
           }
           // forward substitution on the 4-vectors held by this lane
+          const T n10 = -L[1][0], n20 = -L[2][0], n21 = -L[2][1], n30 = -L[3][0], n31 = -L[3][1], n32 = -L[3][2];
           auto fsub = [&](T& x0, T& x1, T& x2, T& x3) {
             x0 = x0 * inv[0];
-            x1 = fma_(-L[1][0], x0, x1) * inv[1];
-            x2 = fma_(-L[2][1], x1, fma_(-L[2][0], x0, x2)) * inv[2];
-            x3 = fma_(-L[3][2], x2, fma_(-L[3][1], x1, fma_(-L[3][0], x0, x3))) * inv[3];
+            x1 = fma_(n10, x0, x1) * inv[1];
+            x2 = fma_(n21, x1, fma_(n20, x0, x2)) * inv[2];
+            x3 = fma_(n32, x2, fma_(n31, x1, fma_(n30, x0, x3))) * inv[3];
           };
+          // the same substitution on two right-hand sides at once (packed pairs, bit-identical per half)
+          auto fsub2 = [&](T& a0, T& b0, T& a1, T& b1, T& a2, T& b2, T& a3, T& b3) {
+            Pair<T> x0 = pair_mul_s(inv[0], pair_make(a0, b0));
+            Pair<T> x1 = pair_mul_s(inv[1], pair_fma_s(n10, x0, pair_make(a1, b1)));
+            Pair<T> x2 = pair_mul_s(inv[2], pair_fma_s(n21, x1, pair_fma_s(n20, x0, pair_make(a2, b2))));
+            Pair<T> x3 = pair_mul_s(inv[3], pair_fma_s(n32, x2, pair_fma_s(n31, x1, pair_fma_s(n30, x0, pair_make(a3, b3)))));
+            pair_get(x0, a0, b0); pair_get(x1, a1, b1); pair_get(x2, a2, b2); pair_get(x3, a3, b3);
+          };
+          if constexpr (TM % 2 == 0 && TN % 2 == 0) {
 #pragma unroll
-          for (int r = 0; r < TM; ++r) fsub(RA[0][r], RA[1][r], RA[2][r], RA[3][r]);
+            for (int r = 0; r < TM; r += 2)
+              fsub2(RA[0][r], RA[0][r + 1], RA[1][r], RA[1][r + 1], RA[2][r], RA[2][r + 1], RA[3][r], RA[3][r + 1]);
 #pragma unroll
-          for (int cc = 0; cc < TN; ++cc) fsub(RC[0][cc], RC[1][cc], RC[2][cc], RC[3][cc]);
+            for (int cc = 0; cc < TN; cc += 2)
+              fsub2(RC[0][cc], RC[0][cc + 1], RC[1][cc], RC[1][cc + 1], RC[2][cc], RC[2][cc + 1], RC[3][cc], RC[3][cc + 1]);
+          } else {
+#pragma unroll
+            for (int r = 0; r < TM; ++r) fsub(RA[0][r], RA[1][r], RA[2][r], RA[3][r]);
+#pragma unroll
+            for (int cc = 0; cc < TN; ++cc) fsub(RC[0][cc], RC[1][cc], RC[2][cc], RC[3][cc]);
+          }
           fsub(v[0], v[1], v[2], v[3]);
 #pragma unroll
           for (int aa = 0; aa < NB; ++aa) {
+            if constexpr (TN % 2 == 0) {
+              Pair<T> nrc[TN / 2];  // -Z[aa, columns of this lane], negated once per block row
 #pragma unroll
-            for (int r = 0; r < TM; ++r) {
+              for (int c2 = 0; c2 < TN / 2; ++c2) nrc[c2] = pair_make(-RC[aa][2 * c2], -RC[aa][2 * c2 + 1]);
 #pragma unroll
-              for (int cc = 0; cc < TN; ++cc) p[r][cc] = fma_(-RA[aa][r], RC[aa][cc], p[r][cc]);
-              mreg[r] = fma_(RA[aa][r], v[aa], mreg[r]);  // only the tx == 0 copies are ever read
+              for (int r = 0; r < TM; ++r) {
+#pragma unroll
+                for (int c2 = 0; c2 < TN / 2; ++c2) {
+                  const Pair<T> pp = pair_fma_s(RA[aa][r], nrc[c2], pair_make(p[r][2 * c2], p[r][2 * c2 + 1]));
+                  pair_get(pp, p[r][2 * c2], p[r][2 * c2 + 1]);
+                }
+                mreg[r] = fma_(RA[aa][r], v[aa], mreg[r]);  // only the tx == 0 copies are ever read
+              }
+            } else {
+#pragma unroll
+              for (int r = 0; r < TM; ++r) {
+#pragma unroll
+                for (int cc = 0; cc < TN; ++cc) p[r][cc] = fma_(-RA[aa][r], RC[aa][cc], p[r][cc]);
+                mreg[r] = fma_(RA[aa][r], v[aa], mreg[r]);  // only the tx == 0 copies are ever read
+              }
             }
             quad = fma_(v[aa], v[aa], quad);
           }

@@ -84,9 +84,21 @@ __device__ __forceinline__ Pair<float> pair_fma(Pair<float> a, Pair<float> b, Pa
 __device__ __forceinline__ Pair<double> pair_fma(Pair<double> a, Pair<double> b, Pair<double> c) {
   return Pair<double>{fma(a.lo, b.lo, c.lo), fma(a.hi, b.hi, c.hi)};
 }
+// a * b, element-wise, and s * b
+__device__ __forceinline__ Pair<float> pair_mul(Pair<float> a, Pair<float> b) {
+  Pair<float> r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ Pair<double> pair_mul(Pair<double> a, Pair<double> b) {
+  return Pair<double>{a.lo * b.lo, a.hi * b.hi};
+}
 // s * b + c with the scalar s applied to both halves (FFMA2 takes it as a broadcast operand, no extra move)
 template <typename T> __device__ __forceinline__ Pair<T> pair_fma_s(T s, Pair<T> b, Pair<T> c) {
   return pair_fma(pair_make(s, s), b, c);
+}
+template <typename T> __device__ __forceinline__ Pair<T> pair_mul_s(T s, Pair<T> b) {
+  return pair_mul(pair_make(s, s), b);
 }
 
 // MODE 0: C = X^T Y ; MODE 1: C = E + X^T Y ; MODE 2: C = E - X^T Y.   K = inner extent.
