@@ -611,19 +611,24 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
     T quad = T(0);
     if constexpr (TM % 4 == 0) {
       constexpr int NB = 4, RS = D + 4;
+      // Blocks are walked lane-row group by lane-row group: the group loop stays rolled (its body, BPG blocks,
+      // is ~1k instructions; unrolling all D / 4 blocks overflowed the instruction cache), the register rows a
+      // block publishes are then compile-time indices hb * NB + aa.
+      constexpr int BPG = TM / NB;
+#pragma unroll 1
+      for (int grp = 0; grp < GY; ++grp) {
 #pragma unroll
-      for (int blk = 0; blk < D / NB; ++blk) {
-        constexpr int dummy = 0; (void)dummy;
-        const int i0 = blk * NB;
+      for (int hb = 0; hb < BPG; ++hb) {
+        const int i0 = (grp * BPG + hb) * NB;
         const unsigned bits = (obs_mask >> i0) & 0xFu;
         if (bits != 0u) {  // warp-uniform
           T* rb = rowbuf + parity * (NB * RS);
           parity ^= 1;
-          if (ty == i0 / TM) {
+          if (ty == grp) {
 #pragma unroll
             for (int aa = 0; aa < NB; ++aa) {
-              stv<T, TN>(rb + aa * RS + tx * TN, p[(i0 % TM) + aa]);
-              if (tx == 0) rb[aa * RS + D] = mreg[(i0 % TM) + aa];
+              stv<T, TN>(rb + aa * RS + tx * TN, p[hb * NB + aa]);
+              if (tx == 0) rb[aa * RS + D] = mreg[hb * NB + aa];
             }
           }
           __syncwarp();
@@ -734,6 +739,7 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
           }
         }
       }
+      }
     } else {
 #pragma unroll
       for (int i0 = 0; i0 < D; i0 += TM) {
@@ -783,8 +789,10 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
     }
     __syncwarp();
     T* Pt = Psg + (int64_t)t * a.d.Ps.time;
-    for (int r = 0; r < d; ++r)
-      if (lane < d) Pt[r * d + lane] = stage[r * LDS_ + lane];
+    if (lane < d) {
+#pragma unroll 6
+      for (int r = 0; r < d; ++r) Pt[r * d + lane] = stage[r * LDS_ + lane];
+    }
     if (lane < d) msg[(int64_t)t * a.d.ms.time + lane] = mvec[lane];
     __syncwarp();
   }
