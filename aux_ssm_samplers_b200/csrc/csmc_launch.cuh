@@ -29,8 +29,9 @@ static int launch_csmc_one(cudaStream_t st, CsmcArgs<T>& a, int max_slots, int* 
   return AUXSSM_OK;
 }
 
-// particle-matrix formulation for wide states (csmc_wide.cuh), instantiated in csmc_wide_*.cu.
-// Returns AUXSSM_WIDE_NA when the shape is outside its domain (d <= 4, N > 256, or shared memory too small).
+// Alternative work decompositions instantiated in csmc_wide_*.cu: the particle-matrix kernel for wide states
+// (csmc_wide.cuh: 4 < d <= 32, N <= 256) and the four-particles-per-thread kernel (csmc_multi.cuh: d <= 4,
+// N > 256, N % 4 == 0).  Returns AUXSSM_WIDE_NA when the shape is in neither domain.
 enum { AUXSSM_WIDE_NA = 1 };
 template <typename T, int PROP> int launch_csmc_wide_family(cudaStream_t st, CsmcArgs<T>& a, int max_slots, int* slots_used);
 

@@ -114,7 +114,7 @@ def compare(state, hist, oracle_out, dtype, C, u_res=None):
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("potential", ["flat", "gaussian", "sv"])
-@pytest.mark.parametrize("d,N,T", [(1, 32, 5), (1, 300, 12), (2, 100, 9), (5, 40, 7), (30, 64, 6)])
+@pytest.mark.parametrize("d,N,T", [(1, 32, 5), (1, 300, 12), (2, 100, 9), (5, 40, 7), (30, 64, 6), (2, 260, 6), (4, 512, 4)])
 @pytest.mark.parametrize("backward", [False, True])
 @pytest.mark.parametrize("resampling", ["multinomial", "killing"])
 def test_bootstrap_sweep_vs_oracle(dtype, potential, d, N, T, backward, resampling):
@@ -147,7 +147,7 @@ def test_bootstrap_sweep_vs_oracle(dtype, potential, d, N, T, backward, resampli
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("kind", ["independent", "independent-grad", "guided"])
-@pytest.mark.parametrize("d,N,T", [(1, 64, 8), (3, 50, 6), (30, 48, 5)])
+@pytest.mark.parametrize("d,N,T", [(1, 64, 8), (3, 50, 6), (30, 48, 5), (3, 320, 4), (1, 1024, 5)])
 @pytest.mark.parametrize("backward", [False, True])
 def test_auxiliary_sweeps_vs_oracle(dtype, kind, d, N, T, backward):
     from aux_ssm_samplers_b200 import csmc
