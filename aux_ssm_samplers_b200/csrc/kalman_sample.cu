@@ -117,12 +117,22 @@ __device__ __forceinline__ void bwd_solve(const T* L, T* B, const T* dg, int n, 
   cta_sync<D>();
 }
 
+// Work items (one warp each) sharing a CTA in the lean one-warp-per-item configuration.  The straight-line body
+// of an item (two unrolled Choleskys, forward / backward substitution) is ~100 KB of SASS, three times the 32 KB
+// instruction cache: warps that drift apart each stream it from L2 (ncu: `no_instruction` was the largest stall).
+// Seven warps per CTA, re-aligned by one block barrier per item, fetch every line once for all seven.
+template <typename T, int D, bool LEAN> struct ElemCfg {
+  static constexpr int W = (LEAN && D <= 32) ? 7 : 1;
+  static constexpr int MINB = (Occ<T, D>::MINB / W) > 0 ? Occ<T, D>::MINB / W : 1;
+};
+
 // pass 1: (G_t^T, e_t) for one unit and a tile of time steps
 template <typename T, int D, bool LEAN>
-__global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) sample_elements_kernel(SampleArgs<T> a) {
+__global__ void __launch_bounds__(Tile<D>::NT * ElemCfg<T, D, LEAN>::W, ElemCfg<T, D, LEAN>::MINB)
+sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* p = reinterpret_cast<T*>(smem_raw);
-  constexpr int NT = Tile<D>::NT, LD = Tile<D>::LD;
+  constexpr int NT = Tile<D>::NT, LD = Tile<D>::LD, W = ElemCfg<T, D, LEAN>::W;
+  T* p = reinterpret_cast<T*>(smem_raw) + (size_t)threadIdx.y * samp_smem_elems<D>(LEAN);
   for (size_t e = threadIdx.x; e < samp_smem_elems<D>(LEAN); e += NT) p[e] = T(0);
   __syncthreads();
   SampBuf<T, D> s;
@@ -140,15 +150,21 @@ __global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) sample_elements_
     }
     __syncthreads();
   }
-  const int ul = blockIdx.x, unit = a.unit0 + ul;
+  // item = (unit, time tile), flattened so that only the last CTA of the grid can be partly filled
+  const int64_t item = (int64_t)blockIdx.x * W + threadIdx.y;
+  const bool live = item < (int64_t)a.n_units * n_tiles;
+  const int ul = live ? (int)(item / n_tiles) : 0, unit = a.unit0 + ul;
   const int c = unit / a.d.n_batch, b = unit % a.d.n_batch;
   const int dx = a.d.dx, Tn = a.d.T, ssz = dx * dx + dx;
-  const int t_lo = blockIdx.y * kTileLen;
+  const int t_lo = live ? (int)(item % n_tiles) * kTileLen : Tn;
   const int t_hi = (t_lo + kTileLen < Tn) ? t_lo + kTileLen : Tn;
   const int i = threadIdx.x;
   bool first_dyn = true;
   int fdiag = 0;  // 0 unknown, 1 diagonal time-invariant F, -1 dense
-  for (int t = t_lo; t < t_hi; ++t) {
+  for (int it = 0; it < kTileLen; ++it) {
+    if (W > 1) __syncthreads();  // keeps the CTA's warps on the same instruction-cache lines
+    const int t = t_lo + it;
+    if (t >= t_hi) { if (W > 1) continue; else break; }
     T* g = a.steps + ((int64_t)ul * Tn + t) * ssz;
     cta_sync<D>();
     if (i < dx) {
@@ -310,7 +326,8 @@ template <typename T, int D> static int launch_sample(cudaStream_t st, SampleArg
   constexpr int NT = Tile<D>::NT;
   const bool lean = (a.d.flags & AUXSSM_FLAG_F_IS_DIAGONAL) != 0 && a.d.T > 1 && a.d.Fs.time == 0 &&
                     a.d.Qs.time == 0 && a.d.bs.time == 0;
-  const size_t smem = samp_smem_elems<D>(lean) * sizeof(T);
+  const int W = lean ? ElemCfg<T, D, true>::W : ElemCfg<T, D, false>::W;
+  const size_t smem = samp_smem_elems<D>(lean) * sizeof(T) * W;
   int rc = lean ? ensure_smem(sample_elements_kernel<T, D, true>, smem, "auxssm_kalman_sample")
                 : ensure_smem(sample_elements_kernel<T, D, false>, smem, "auxssm_kalman_sample");
   if (rc) return rc;
@@ -318,8 +335,9 @@ template <typename T, int D> static int launch_sample(cudaStream_t st, SampleArg
   for (int u0 = 0; u0 < units; u0 += wave) {
     a.unit0 = u0;
     a.n_units = (units - u0 < wave) ? units - u0 : wave;
-    if (lean) sample_elements_kernel<T, D, true><<<dim3(a.n_units, n_tiles), NT, smem, st>>>(a);
-    else sample_elements_kernel<T, D, false><<<dim3(a.n_units, n_tiles), NT, smem, st>>>(a);
+    const unsigned grid = (unsigned)(((int64_t)a.n_units * n_tiles + W - 1) / W);
+    if (lean) sample_elements_kernel<T, D, true><<<grid, dim3(NT, W), smem, st>>>(a, n_tiles);
+    else sample_elements_kernel<T, D, false><<<grid, dim3(NT, W), smem, st>>>(a, n_tiles);
     AUXSSM_CHECK_LAUNCH("auxssm_kalman_sample (elements)");
     sample_replay_kernel<T, D><<<a.n_units, 64, 0, st>>>(a);
     AUXSSM_CHECK_LAUNCH("auxssm_kalman_sample (replay)");
