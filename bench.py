@@ -354,7 +354,7 @@ def run_gpu(args):
             "alg_bytes_per_unit": cnd["bytes_unit"], "survey_bytes_per_unit": cnd["survey_bytes_unit"],
             "share_of_step": ms_tot / step_ms_local,
             "fp32_tflops_achieved": cnd["flops_unit"] * units_launch / (per * 1e-3) / 1e12,
-            "note": "FP32-FMA / issue bound, not HBM bound (see DESIGN.md section 4); traffic from ncu in profiles/",
+            "note": "FP32 issue / dependent-chain latency bound, not HBM bound (DESIGN.md section 4); traffic = ncu DRAM bytes of the call's dominant kernel (for the sampler: P_t in + the (G_t, e_t) scratch out, which the replay kernel reads back)",
         })
     roofs.sort(key=lambda r: -r["share_of_step"])
     roofline = roofs[0] if roofs else None
