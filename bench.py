@@ -344,20 +344,33 @@ def run_gpu(args):
         if not calls:
             continue
         per = ms_tot / calls
-        ach = cnd["bytes_unit"] * units_launch / (per * 1e-3) / 1e9
+        # `achieved` uses SURVEY.md section 8(d)'s operator-boundary bytes per (time-step x chain) for this call, as the
+        # bench contract asks; the bytes this kernel's own interface moves (F, Q, b, H are stride-0 broadcasts, R_t is
+        # diagonal) are reported beside it as `interface_*` -- the fused figure "in addition, never instead".
+        ach = cnd["survey_bytes_unit"] * units_launch / (per * 1e-3) / 1e9
+        ach_if = cnd["bytes_unit"] * units_launch / (per * 1e-3) / 1e9
         roofs.append({
             "bound": "hbm", "kernel": cnd["kernel"] + " (" + name + ")", "achieved": ach, "peak": peak_hbm,
             "unit": "GB/s", "frac": ach / peak_hbm,
             "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
             "traffic": ncu_traffic(cnd["kernel"]), "traffic_source": "profiles/traffic_r1.json (ncu --set full)",
             "ms_per_launch": per, "launches_timed": calls,
-            "alg_bytes_per_unit": cnd["bytes_unit"], "survey_bytes_per_unit": cnd["survey_bytes_unit"],
+            "alg_bytes_per_unit": cnd["survey_bytes_unit"], "units_per_launch": units_launch,
+            "interface_bytes_per_unit": cnd["bytes_unit"], "interface_achieved": ach_if,
+            "interface_frac": ach_if / peak_hbm,
             "share_of_step": ms_tot / step_ms_local,
             "fp32_tflops_achieved": cnd["flops_unit"] * units_launch / (per * 1e-3) / 1e12,
-            "note": "FP32 issue / dependent-chain latency bound, not HBM bound (DESIGN.md section 4); traffic = ncu DRAM bytes of the call's dominant kernel (for the sampler: P_t in + the (G_t, e_t) scratch out, which the replay kernel reads back)",
+            "note": "FP32 issue / dependent-chain latency bound, not HBM bound (DESIGN.md section 4); traffic = ncu DRAM "
+                    "bytes of the call's dominant kernel (for the sampler: P_t in + the (G_t, e_t) scratch out, which "
+                    "the replay kernel reads back)",
         })
     roofs.sort(key=lambda r: -r["share_of_step"])
     roofline = roofs[0] if roofs else None
+    if roofline is not None:
+        sweep_bytes = (21 * d * d + 20 * d) * es  # whole sweep, operator-boundary traffic
+        roofline["sweep"] = {"alg_bytes_per_unit": sweep_bytes,
+                             "achieved": sweep_bytes * units_launch / (step_ms_local * 1e-3) / 1e9, "unit": "GB/s"}
+        roofline["sweep"]["frac"] = roofline["sweep"]["achieved"] / peak_hbm
     roofline_other = roofs[1:] if len(roofs) > 1 else []
     kernel_ms = {k: {"calls": v[0], "ms_total": v[1]} for k, v in sorted(summ.items())}
 
@@ -402,7 +415,7 @@ def run_gpu(args):
                        "delta": delta, "parallel": True,
                        "R_layout": "dense [C,T,d,d]" if args.dense_r else "diagonal [C,T,d] (Omega_t is diagonal)",
                        "time_chunks": "auto (=1: 1024 chains fill the SMs; see DESIGN.md)",
-                       "l2": "inputs (>=3.7 GB of R_t per filter) exceed the 126 MB L2; no flush needed",
+                       "l2": "every kernel streams more than the 126 MB L2 per launch (P_t history 3.9 GB, states / draws 126 MB each); no flush needed",
                        "draws": "externally supplied normals/uniforms (parity mode), 2 rotating sets"},
             "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "roofline_other": roofline_other, "kernel_ms": kernel_ms,
