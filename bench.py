@@ -369,7 +369,8 @@ def run_gpu(args):
     if roofline is not None:
         sweep_bytes = (21 * d * d + 20 * d) * es  # whole sweep, operator-boundary traffic
         roofline["sweep"] = {"alg_bytes_per_unit": sweep_bytes,
-                             "achieved": sweep_bytes * units_launch / (step_ms_local * 1e-3) / 1e9, "unit": "GB/s"}
+                             "achieved": sweep_bytes * units_launch / (step_ms_local / args.steps * 1e-3) / 1e9,
+                             "unit": "GB/s"}
         roofline["sweep"]["frac"] = roofline["sweep"]["achieved"] / peak_hbm
     roofline_other = roofs[1:] if len(roofs) > 1 else []
     kernel_ms = {k: {"calls": v[0], "ms_total": v[1]} for k, v in sorted(summ.items())}
