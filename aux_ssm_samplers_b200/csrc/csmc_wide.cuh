@@ -34,12 +34,6 @@ template <typename T, int D> struct WideCfg {
   static_assert(CT >= 1 && CT <= NW && NW % CT == 0, "unsupported D");
 };
 
-template <int BYTES> __device__ __forceinline__ void cp_async(void* smem, const void* g) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(g), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
 // compact global [rows][d] -> padded shared [rows][LD], element-wise asynchronous copies.
 // magic = 2^32 / d + 1 gives e / d exactly for e < 2^13, d <= 32.
 // Even d: two elements per copy (rows then start on 2-element boundaries on both sides).

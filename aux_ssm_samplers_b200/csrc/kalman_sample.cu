@@ -161,17 +161,35 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
   const int i = threadIdx.x;
   bool first_dyn = true;
   int fdiag = 0;  // 0 unknown, 1 diagonal time-invariant F, -1 dense
+  // PAD path: P_t of the NEXT item is requested (cp.async) into the S buffer as soon as chol(S) has been used for
+  // the last time, a quarter of an item ahead of its use; the two buffers then swap roles.  No DRAM round trip
+  // on the per-item critical path and no extra shared memory.  m_t / eps_t travel through two registers.
+  const T* Pg = a.Ps + unit_off(a.d.Ps, c, b);
+  const T* mg = a.ms + unit_off(a.d.ms, c, b);
+  const T* eg = a.eps + unit_off(a.d.eps, c, b);
+  T m_n = T(0), e_n = T(0);
+  if (PAD && t_lo < t_hi) {
+    warp_stage_mat_async<T, LD>(s.S, Pg + (int64_t)t_lo * a.d.Ps.time, dx);
+    if (i < dx) { m_n = mg[(int64_t)t_lo * a.d.ms.time + i]; e_n = eg[(int64_t)t_lo * a.d.eps.time + i]; }
+  }
   for (int it = 0; it < kTileLen; ++it) {
     if (W > 1) __syncthreads();  // keeps the CTA's warps on the same instruction-cache lines
     const int t = t_lo + it;
     if (t >= t_hi) { if (W > 1) continue; else break; }
     T* g = a.steps + ((int64_t)ul * Tn + t) * ssz;
     cta_sync<D>();
-    if (i < dx) {
-      s.m[i] = a.ms[unit_off(a.d.ms, c, b) + (int64_t)t * a.d.ms.time + i];
-      s.eps[i] = a.eps[unit_off(a.d.eps, c, b) + (int64_t)t * a.d.eps.time + i];
+    if (PAD) {
+      cp_async_wait_all();
+      T* sw = s.P; s.P = s.S; s.S = sw;
+      if (i < dx) { s.m[i] = m_n; s.eps[i] = e_n; }
+      cta_sync<D>();
+    } else {
+      if (i < dx) {
+        s.m[i] = mg[(int64_t)t * a.d.ms.time + i];
+        s.eps[i] = eg[(int64_t)t * a.d.eps.time + i];
+      }
+      load_mat<T, D, false>(Pg + (int64_t)t * a.d.Ps.time, s.P, dx, dx);
     }
-    load_mat<T, D, false>(a.Ps + unit_off(a.d.Ps, c, b) + (int64_t)t * a.d.Ps.time, s.P, dx, dx);
     if (t == Tn - 1) {
       // last step: x_{T-1} = m + chol(P) eps  (sampling.py:116-124)
       chol_nan_to_zero<T, D, PAD>(s.P, s.dg, dx);
@@ -230,6 +248,10 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
     fwd_solve<T, D, PAD>(s.S, s.Z, nullptr, dx, dx, s.dg);  // Zs = Ls^{-1} F P
     mm_tn<T, D, 2>(s.Z, s.Z, s.P, s.P, PAD ? D : dx);       // Sigma = P - Zs^T Zs  (lower triangle feeds the Cholesky)
     bwd_solve<T, D, PAD>(s.S, s.Z, s.dg, dx, dx);           // Z <- G^T = Ls^{-T} Zs
+    if (PAD && t + 1 < t_hi) {                              // chol(S) is dead: its buffer receives P_{t+1}
+      warp_stage_mat_async<T, LD>(s.S, Pg + (int64_t)(t + 1) * a.d.Ps.time, dx);
+      if (i < dx) { m_n = mg[(int64_t)(t + 1) * a.d.ms.time + i]; e_n = eg[(int64_t)(t + 1) * a.d.eps.time + i]; }
+    }
     chol_nan_to_zero<T, D, PAD>(s.P, s.dg, dx);             // L = chol(Sigma), NaN -> 0
     if (PAD) {
       mv_tn_pad<T, D, 2>(s.Z, s.r, s.e, s.m);               // e = m - G (F m + b)     (G v = (G^T)^T v)

@@ -101,6 +101,33 @@ template <typename T> __device__ __forceinline__ Pair<T> pair_mul_s(T s, Pair<T>
   return pair_mul(pair_make(s, s), b);
 }
 
+// Ampere-style asynchronous global -> shared copies (LDGSTS): the data lands in shared memory without passing
+// through registers and without stalling the issuing warp; `cp_async_wait_all` + a barrier publish it.
+template <int BYTES> __device__ __forceinline__ void cp_async(void* smem, const void* g) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(g), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// One warp: compact global [d][d] -> padded shared [d][LD] (LD even), asynchronously.  Even d: 2 elements per copy.
+template <typename T, int LD> __device__ __forceinline__ void warp_stage_mat_async(T* dst, const T* src, int d) {
+  const unsigned magic = 0xffffffffu / (unsigned)d + 1u;  // e / d exactly for e < 2^13, d <= 32
+  const int lane = threadIdx.x & 31, total = d * d;
+  if ((d & 1) == 0 && (reinterpret_cast<uintptr_t>(src) % (2 * sizeof(T))) == 0) {
+#pragma unroll 4
+    for (int e = 2 * lane; e < total; e += 64) {
+      const int n = (int)__umulhi((unsigned)e, magic), k = e - n * d;
+      cp_async<2 * sizeof(T)>(dst + n * LD + k, src + e);
+    }
+  } else {
+#pragma unroll 4
+    for (int e = lane; e < total; e += 32) {
+      const int n = (int)__umulhi((unsigned)e, magic), k = e - n * d;
+      cp_async<sizeof(T)>(dst + n * LD + k, src + e);
+    }
+  }
+}
+
 // MODE 0: C = X^T Y ; MODE 1: C = E + X^T Y ; MODE 2: C = E - X^T Y.   K = inner extent.
 // X, Y, C, E are D x LD shared buffers; C may alias E but must not alias X or Y.
 template <typename T, int D, int MODE>
