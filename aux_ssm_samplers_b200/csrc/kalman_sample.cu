@@ -117,6 +117,51 @@ __device__ __forceinline__ void bwd_solve(const T* L, T* B, const T* dg, int n, 
   cta_sync<D>();
 }
 
+// One-warp vectorised passes of the lean path (even dx): a lane owns four consecutive columns of a row, 32 / (D / 4)
+// rows per pass; shared accesses are 16-byte vectors, the compact global rows (dx elements, 2-element aligned) move
+// as 2-element vectors.
+// S_ab = f_a f_b P_ab + Q_ab,  Z_ab = f_a P_ab  (time-invariant diagonal F; fd is zero beyond dx)
+template <typename T, int D>
+__device__ __forceinline__ void lean_predict_rows(const T* P, const T* fd, const T* __restrict__ Qg, T* S, T* Z, int dx) {
+  constexpr int LD = Tile<D>::LD, LPR = D / 4, RPP = 32 / LPR;
+  const int lane = threadIdx.x & 31, lr = lane / LPR, c4 = (lane % LPR) * 4;
+  T fc[4];
+  ldv<T, 4>(fc, fd + c4);
+#pragma unroll 4
+  for (int r0 = 0; r0 < dx; r0 += RPP) {
+    const int r = r0 + lr;
+    if (r < dx) {
+      T pv[4], qa[2] = {T(0), T(0)}, qb[2] = {T(0), T(0)}, s4[4], z4[4];
+      ldv<T, 4>(pv, P + r * LD + c4);
+      if (c4 < dx) ldv<T, 2>(qa, Qg + r * dx + c4);
+      if (c4 + 2 < dx) ldv<T, 2>(qb, Qg + r * dx + c4 + 2);
+      const T fa = fd[r];
+      s4[0] = fma_(fa * fc[0], pv[0], qa[0]); s4[1] = fma_(fa * fc[1], pv[1], qa[1]);
+      s4[2] = fma_(fa * fc[2], pv[2], qb[0]); s4[3] = fma_(fa * fc[3], pv[3], qb[1]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) z4[q] = fa * pv[q];
+      stv<T, 4>(S + r * LD + c4, s4);
+      stv<T, 4>(Z + r * LD + c4, z4);
+    }
+  }
+}
+// global [dx x dx] <- shared [dx x LD]
+template <typename T, int D> __device__ __forceinline__ void store_rows_pairs(T* __restrict__ g, const T* s, int dx) {
+  constexpr int LD = Tile<D>::LD, LPR = D / 4, RPP = 32 / LPR;
+  const int lane = threadIdx.x & 31, lr = lane / LPR, c4 = (lane % LPR) * 4;
+#pragma unroll 4
+  for (int r0 = 0; r0 < dx; r0 += RPP) {
+    const int r = r0 + lr;
+    if (r < dx) {
+      T v[4];
+      ldv<T, 4>(v, s + r * LD + c4);
+      const T va[2] = {v[0], v[1]}, vb[2] = {v[2], v[3]};
+      if (c4 < dx) stv<T, 2>(g + r * dx + c4, va);
+      if (c4 + 2 < dx) stv<T, 2>(g + r * dx + c4 + 2, vb);
+    }
+  }
+}
+
 // Work items (one warp each) sharing a CTA in the lean one-warp-per-item configuration.  The straight-line body
 // of an item (two unrolled Choleskys, forward / backward substitution) is ~100 KB of SASS, three times the 32 KB
 // instruction cache: warps that drift apart each stream it from L2 (ncu: `no_instruction` was the largest stall).
@@ -168,6 +213,10 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
   const T* mg = a.ms + unit_off(a.d.ms, c, b);
   const T* eg = a.eps + unit_off(a.d.eps, c, b);
   T m_n = T(0), e_n = T(0);
+  // 2-element vector accesses to the compact global rows need even dx and 2-element aligned bases
+  const bool pairs_ok = PAD && (dx & 1) == 0 && a.Qs != nullptr &&
+                        (reinterpret_cast<uintptr_t>(a.Qs + unit_off(a.d.Qs, c, b)) % (2 * sizeof(T))) == 0 &&
+                        (reinterpret_cast<uintptr_t>(a.steps) % (2 * sizeof(T))) == 0;
   if (PAD && t_lo < t_hi) {
     warp_stage_mat_async<T, LD>(s.S, Pg + (int64_t)t_lo * a.d.Ps.time, dx);
     if (i < dx) { m_n = mg[(int64_t)t_lo * a.d.ms.time + i]; e_n = eg[(int64_t)t_lo * a.d.eps.time + i]; }
@@ -206,10 +255,14 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
         first_dyn = false;
       }
       cta_sync<D>();
-      AUXSSM_FOR_ROWS(ri, rj, dx, dx) {
-        const T fa = fd[ri], pv = s.P[ri * LD + rj];
-        s.S[ri * LD + rj] = fma_(fa * fd[rj], pv, Qg[ri * dx + rj]);
-        s.Z[ri * LD + rj] = fa * pv;
+      if (PAD && pairs_ok) {
+        lean_predict_rows<T, D>(s.P, fd, Qg, s.S, s.Z, dx);
+      } else {
+        AUXSSM_FOR_ROWS(ri, rj, dx, dx) {
+          const T fa = fd[ri], pv = s.P[ri * LD + rj];
+          s.S[ri * LD + rj] = fma_(fa * fd[rj], pv, Qg[ri * dx + rj]);
+          s.Z[ri * LD + rj] = fa * pv;
+        }
       }
       if (i < dx) s.r[i] = fma_(fd[i], s.m[i], s.bv[i]);
       cta_sync<D>();
@@ -260,7 +313,7 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
       mv_tn<T, D, 2>(s.Z, s.r, s.e, s.m, dx, dx);
       mv_nn<T, D, 1>(s.P, s.eps, s.e, s.e, dx, dx);
     }
-    store_mat<T, D>(g, s.Z, dx, dx);
+    if (PAD && pairs_ok) store_rows_pairs<T, D>(g, s.Z, dx); else store_mat<T, D>(g, s.Z, dx, dx);
     if (i < dx) g[dx * dx + i] = s.e[i];
   }
 }
