@@ -561,6 +561,8 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
   const T* cg = a.cs ? a.cs + unit_off(a.d.cs, c, b) : nullptr;
   T* msg = a.ms + unit_off(a.d.ms, c, b);
   T* Psg = a.Ps + unit_off(a.d.Ps, c, b);
+  const bool pairs_ok = (d & 1) == 0 && (a.d.Ps.time & 1) == 0 &&
+                        (reinterpret_cast<uintptr_t>(Psg) % (2 * sizeof(T))) == 0;
   // prefetch the first step's observation
   T y_n = T(0), r_n = T(1), c_n = T(0);
   if (lane < d) {
@@ -789,7 +791,22 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
     }
     __syncwarp();
     T* Pt = Psg + (int64_t)t * a.d.Ps.time;
-    if (lane < d) {
+    if (pairs_ok) {
+      // a lane owns four consecutive columns of a row (16-byte shared load, two 2-element global stores)
+      constexpr int LPR = D / 4, RPP = 32 / LPR;
+      const int lr = lane / LPR, c4 = (lane % LPR) * 4;
+#pragma unroll 4
+      for (int r0 = 0; r0 < d; r0 += RPP) {
+        const int r = r0 + lr;
+        if (r < d) {
+          T v[4];
+          ldv<T, 4>(v, stage + r * LDS_ + c4);
+          const T va[2] = {v[0], v[1]}, vb[2] = {v[2], v[3]};
+          if (c4 < d) stv<T, 2>(Pt + r * d + c4, va);
+          if (c4 + 2 < d) stv<T, 2>(Pt + r * d + c4 + 2, vb);
+        }
+      }
+    } else if (lane < d) {
 #pragma unroll 6
       for (int r = 0; r < d; ++r) Pt[r * d + lane] = stage[r * LDS_ + lane];
     }
