@@ -823,6 +823,10 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
   if (lane == 0) a.ellpart[(int64_t)unit * a.n_chunks + j] = ell;
 }
 
+}  // namespace auxssm
+#include "kalman_filter_tile.cuh"
+namespace auxssm {
+
 // ---- parallel-in-time: elements and the associative combine ------------------------------------
 
 template <typename T, int D> struct ScanBuf {
@@ -1062,9 +1066,17 @@ static int launch_filter(cudaStream_t st, const FilterArgs<T>& a) {
   const uint32_t need = AUXSSM_FLAG_H_IDENTITY | AUXSSM_FLAG_R_DIAGONAL | AUXSSM_FLAG_F_IS_DIAGONAL;
   const bool warp_path = D >= 8 && D <= 32 && (a.d.flags & need) == need &&
                          (a.d.T == 1 || (a.d.Fs.time == 0 && a.d.Qs.time == 0 && a.d.bs.time == 0));
+  // same structure at D = 64: four warps per chain (kalman_filter_tile.cuh)
+  const bool tile_path = D == 64 && (a.d.flags & need) == need &&
+                         (a.d.T == 1 || (a.d.Fs.time == 0 && a.d.Qs.time == 0 && a.d.bs.time == 0));
+  constexpr int TD = (D == 64) ? 64 : 64, TNW = 4;
+  const size_t smem_tile = filter_tile_smem_elems<TD, TNW>() * sizeof(T);
   if (warp_path) {
     filter_warp_kernel<T, (D >= 8 && D <= 32) ? D : 8><<<dim3((units + 3) / 4, 1), 128, 0, st>>>(a, 0);
     AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (warp recursion, chunk 0)");
+  } else if (tile_path) {
+    filter_tile_kernel<T, TD, TNW><<<dim3(units, 1), 128, smem_tile, st>>>(a, 0);
+    AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (tile recursion, chunk 0)");
   } else {
     rec<<<dim3(units, 1), NT, smem_step, st>>>(a, 0);
     AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (recursion, chunk 0)");
@@ -1084,6 +1096,9 @@ static int launch_filter(cudaStream_t st, const FilterArgs<T>& a) {
     if (warp_path) {
       filter_warp_kernel<T, (D >= 8 && D <= 32) ? D : 8><<<dim3((units + 3) / 4, a.n_chunks - 1), 128, 0, st>>>(a, 1);
       AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (warp recursion, chunks >= 1)");
+    } else if (tile_path) {
+      filter_tile_kernel<T, TD, TNW><<<dim3(units, a.n_chunks - 1), 128, smem_tile, st>>>(a, 1);
+      AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (tile recursion, chunks >= 1)");
     } else {
       rec<<<dim3(units, a.n_chunks - 1), NT, smem_step, st>>>(a, 1);
       AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (recursion, chunks >= 1)");

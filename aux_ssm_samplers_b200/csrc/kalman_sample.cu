@@ -77,7 +77,7 @@ __device__ __forceinline__ void bwd_solve(const T* L, T* B, const T* dg, int n, 
   cta_sync<D>();
   const int j = threadIdx.x;
   if (j < m) {
-    if constexpr (D <= 32) {
+    if constexpr (D <= 64) {
       constexpr int V = (D >= 4) ? 4 : D;
       const T* dginv = dg + D;
       T z[D];

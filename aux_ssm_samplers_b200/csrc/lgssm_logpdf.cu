@@ -319,9 +319,9 @@ struct LogpdfPlan {
 
 constexpr int kFastThreads = 128;
 
-static bool logpdf_fast_ok(const auxssm_lgssm_desc* d, uint32_t which) {
+static bool logpdf_fast_ok(const auxssm_lgssm_desc* d, size_t es, uint32_t which) {
   const int dmax = d->dx > d->dy ? d->dx : d->dy;
-  if (dmax > 32) return false;
+  if (dmax > 64 || (dmax > 32 && es > 4)) return false;  // d = 64: fp32 only (F and chol(Q) in 32 KB static smem)
   if ((which & AUXSSM_LOGPDF_PRIOR) && d->T > 1 && (d->Fs.time != 0 || d->Qs.time != 0 || d->bs.time != 0))
     return false;
   if (which & AUXSSM_LOGPDF_LOGLIK) {
@@ -334,7 +334,7 @@ static bool logpdf_fast_ok(const auxssm_lgssm_desc* d, uint32_t which) {
 static LogpdfPlan make_logpdf_plan(const auxssm_lgssm_desc* d, size_t es, uint32_t which) {
   LogpdfPlan p;
   const long units = (long)d->n_chains * d->n_batch;
-  p.fast = logpdf_fast_ok(d, which);
+  p.fast = logpdf_fast_ok(d, es, which);
   if (p.fast) {
     p.tile_len = kFastThreads;
     p.n_tiles = (d->T + kFastThreads - 1) / kFastThreads;
@@ -414,6 +414,9 @@ static int logpdf_entry(void* stream, const auxssm_lgssm_desc* d, uint32_t which
     case -8: rc = launch_logpdf_fast<T, 8>(st, a, prep); break;
     case -16: rc = launch_logpdf_fast<T, 16>(st, a, prep); break;
     case -32: rc = launch_logpdf_fast<T, 32>(st, a, prep); break;
+    case -64:
+      if constexpr (sizeof(T) == 4) { rc = launch_logpdf_fast<T, 64>(st, a, prep); break; }
+      set_error("%s: internal dispatch error", who); return AUXSSM_ERR_UNSUPPORTED;
     case 4: rc = launch_logpdf<T, 4>(st, a); break;
     case 8: rc = launch_logpdf<T, 8>(st, a); break;
     case 16: rc = launch_logpdf<T, 16>(st, a); break;

@@ -24,7 +24,10 @@ template <> struct Tile<16> { static constexpr int LD = 20, NT = 32,  TM = 2, TN
 // D = 32 runs as ONE warp per work item (8 x 4 register tiles, __syncwarp only): with two warps one of them
 // idled at a block barrier during every Cholesky / triangular-solve phase.
 template <> struct Tile<32> { static constexpr int LD = 36, NT = 32,  TM = 8, TN = 4; };
-template <> struct Tile<64> { static constexpr int LD = 68, NT = 256, TM = 4, TN = 4; };
+// D = 64: two warps per work item.  The factorisations and substitutions keep one warp / one thread per column
+// busy whatever the CTA size, so a 256-thread CTA (255 registers: one CTA per SM) left 7 of its 8 warps at a
+// barrier 90 % of the time; 64 threads leave room for four items per SM (shared-memory bound).
+template <> struct Tile<64> { static constexpr int LD = 68, NT = 64, TM = 8, TN = 8; };  // one 8 x 8 register tile per thread
 
 // Resident CTAs per SM the kernels are compiled for: caps registers at 128/thread for D <= 32 so that
 // 7-8 chains per SM stay co-resident (1024 chains = one wave on 148 SMs).
@@ -522,16 +525,97 @@ template <typename T, int D> __device__ __forceinline__ void fwd_solve_generic(c
 // Workspace convention: a "dg" buffer is 4*D words = [diag(L) | 1/diag(L) | 2*D column exchange].
 template <int D> struct CholWs { static constexpr int WORDS = 4 * D; };
 
+// Register-resident Cholesky for D = 64: warp 0 only, lane l owns rows l (columns 0..31 suffice: lower triangle) and
+// l + 32 (all 64 columns); same column-exchange scheme as chol_reg.  The 256-thread generic version spent its time
+// in 64 block barriers and 8-way bank conflicts (one thread per row, row stride 68 words).
+template <typename T, bool PADDED = false>
+__device__ __forceinline__ void chol_reg64(T* A, T* dg, T* dginv, T* colbuf, int n) {
+  constexpr int D = 64, H = 32, LD = Tile<D>::LD, V = 4;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    T r0[H], r1[D];
+#pragma unroll
+    for (int j = 0; j < D; j += V) {
+      T t0[V], t1[V];
+      if (j < H) ldv<T, V>(t0, A + lane * LD + j);
+      ldv<T, V>(t1, A + (lane + H) * LD + j);
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        if (j < H) r0[j + q] = (PADDED || lane < n) ? t0[q] : T(0);
+        r1[j + q] = (PADDED || lane + H < n) ? t1[q] : T(0);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      if (PADDED || k < n) {
+        const T akk = (k < H) ? __shfl_sync(0xffffffffu, r0[k < H ? k : 0], k & 31)
+                              : __shfl_sync(0xffffffffu, r1[k], k & 31);
+        T lkk, inv;
+        pivot_<T>(akk, lkk, inv);
+        T* cb = colbuf + (k & 1) * D;
+        T l0 = T(0);
+        if (k < H) {
+          l0 = (lane == k) ? lkk : r0[k < H ? k : 0] * inv;
+          r0[k < H ? k : 0] = l0;
+          cb[lane] = l0;
+        }
+        const T l1 = (k >= H && lane == k - H) ? lkk : r1[k] * inv;
+        r1[k] = l1;
+        cb[lane + H] = l1;
+        if ((k < H && lane == k) || (k >= H && lane == k - H)) { dg[k] = lkk; dginv[k] = inv; }
+        __syncwarp();
+        const T nl0 = -l0, nl1 = -l1;
+#pragma unroll
+        for (int j = ((k + 1) / V) * V; j < D; j += V) {
+          T c[V];
+          ldv<T, V>(c, cb + j);
+#pragma unroll
+          for (int q = 0; q < V; q += 2) {
+            if (j + q > k) {
+              const Pair<T> c2 = pair_make(c[q], c[q + 1]);
+              if (j < H && k < H) {
+                const Pair<T> a2 = pair_fma_s(nl0, c2, pair_make(r0[j < H ? j + q : 0], r0[j < H ? j + q + 1 : 1]));
+                pair_get(a2, r0[j < H ? j + q : 0], r0[j < H ? j + q + 1 : 1]);
+              }
+              const Pair<T> b2 = pair_fma_s(nl1, c2, pair_make(r1[j + q], r1[j + q + 1]));
+              pair_get(b2, r1[j + q], r1[j + q + 1]);
+            } else {
+              if (j + q + 1 > k) {
+                if (j < H && k < H) r0[j < H ? j + q + 1 : 1] = fma_(nl0, c[q + 1], r0[j < H ? j + q + 1 : 1]);
+                r1[j + q + 1] = fma_(nl1, c[q + 1], r1[j + q + 1]);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < D; j += V) {
+      T t0[V], t1[V];
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        t0[q] = (j < H && j + q <= lane) ? r0[j < H ? j + q : 0] : T(0);
+        t1[q] = (j + q <= lane + H) ? r1[j + q] : T(0);
+      }
+      if (PADDED || lane < n) stv<T, V>(A + lane * LD + j, t0);
+      if (PADDED || lane + H < n) stv<T, V>(A + (lane + H) * LD + j, t1);
+    }
+  }
+  __syncthreads();
+}
+
 // In-place lower Cholesky of the n x n block; strict upper triangle zeroed; non-PD pivots give NaN.
 template <typename T, int D, bool PADDED = false> __device__ __forceinline__ void chol_inplace(T* A, T* dg, int n) {
   if constexpr (D <= 32) chol_reg<T, D, PADDED>(A, dg, dg + D, dg + 2 * D, n);
+  else if constexpr (D == 64 && Tile<D>::NT >= 32) chol_reg64<T, PADDED>(A, dg, dg + D, dg + 2 * D, n);
   else chol_generic<T, D>(A, dg, n);
 }
 // Z = L^{-1} B in place (n x m block) and optionally bvec <- L^{-1} bvec; `dg` is the workspace the
 // factorisation of L filled.
 template <typename T, int D, bool PADDED = false>
 __device__ __forceinline__ void fwd_solve(const T* L, T* B, T* bvec, int n, int m, const T* dg) {
-  if constexpr (D <= 32) fwd_solve_reg<T, D, PADDED>(L, B, bvec, dg + D, n, m);
+  if constexpr (D <= 64) fwd_solve_reg<T, D, PADDED>(L, B, bvec, dg + D, n, m);  // D = 64: one thread per column
   else fwd_solve_generic<T, D>(L, B, bvec, n, m);
 }
 
@@ -679,7 +763,9 @@ __device__ __forceinline__ void lu_solve(const T* LU, const int* perm, const T* 
       for (int k = i + 1; k < n; ++k) acc = fma_(-LU[i * LD + k], X[k * LD + j], acc);
       X[i * LD + j] = acc / LU[i * LD + i];
     }
-  } else if (j == m && bvec != nullptr) {
+  }
+  // the extra vector: thread m, or thread 0 after its column when the CTA has no spare thread (m >= NT)
+  if (bvec != nullptr && (j == m || (m >= Tile<D>::NT && j == 0))) {
     for (int i = 0; i < n; ++i) {
       T acc = bvec[perm[i]];
       for (int k = 0; k < i; ++k) acc = fma_(-LU[i * LD + k], xvec[k], acc);

@@ -255,7 +255,7 @@ def test_filter_and_logpdf_diagonal_R(dtype, d, T, C, dense_h, chunks, fkind):
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-@pytest.mark.parametrize("d,T,C", [(1, 5, 2), (4, 300, 3), (30, 130, 2)])
+@pytest.mark.parametrize("d,T,C", [(1, 5, 2), (4, 300, 3), (30, 130, 2), (64, 140, 2)])
 def test_logpdf_fast_path_time_invariant(dtype, d, T, C):
     """Time-invariant (stride-0) dynamics + H = I + diagonal R take the thread-per-time-step kernel."""
     from aux_ssm_samplers_b200 import kalman
