@@ -546,24 +546,21 @@ __device__ __forceinline__ void chol_reg64(T* A, T* dg, T* dginv, T* colbuf, int
         r1[j + q] = (PADDED || lane + H < n) ? t1[q] : T(0);
       }
     }
+    // columns 0..31: pivot in row k of the first row set; both row sets are updated
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
+    for (int k = 0; k < H; ++k) {
       if (PADDED || k < n) {
-        const T akk = (k < H) ? __shfl_sync(0xffffffffu, r0[k < H ? k : 0], k & 31)
-                              : __shfl_sync(0xffffffffu, r1[k], k & 31);
+        const T akk = __shfl_sync(0xffffffffu, r0[k], k);
         T lkk, inv;
         pivot_<T>(akk, lkk, inv);
         T* cb = colbuf + (k & 1) * D;
-        T l0 = T(0);
-        if (k < H) {
-          l0 = (lane == k) ? lkk : r0[k < H ? k : 0] * inv;
-          r0[k < H ? k : 0] = l0;
-          cb[lane] = l0;
-        }
-        const T l1 = (k >= H && lane == k - H) ? lkk : r1[k] * inv;
+        const T l0 = (lane == k) ? lkk : r0[k] * inv;
+        const T l1 = r1[k] * inv;
+        r0[k] = l0;
         r1[k] = l1;
+        cb[lane] = l0;
         cb[lane + H] = l1;
-        if ((k < H && lane == k) || (k >= H && lane == k - H)) { dg[k] = lkk; dginv[k] = inv; }
+        if (lane == k) { dg[k] = lkk; dginv[k] = inv; }
         __syncwarp();
         const T nl0 = -l0, nl1 = -l1;
 #pragma unroll
@@ -572,19 +569,47 @@ __device__ __forceinline__ void chol_reg64(T* A, T* dg, T* dginv, T* colbuf, int
           ldv<T, V>(c, cb + j);
 #pragma unroll
           for (int q = 0; q < V; q += 2) {
-            if (j + q > k) {
+            if (j + q > k) {  // both columns of the pair are open: packed FMAs
               const Pair<T> c2 = pair_make(c[q], c[q + 1]);
-              if (j < H && k < H) {
-                const Pair<T> a2 = pair_fma_s(nl0, c2, pair_make(r0[j < H ? j + q : 0], r0[j < H ? j + q + 1 : 1]));
-                pair_get(a2, r0[j < H ? j + q : 0], r0[j < H ? j + q + 1 : 1]);
+              if (j + q + 1 < H) {
+                const Pair<T> a2 = pair_fma_s(nl0, c2, pair_make(r0[(j + q) & (H - 1)], r0[(j + q + 1) & (H - 1)]));
+                pair_get(a2, r0[(j + q) & (H - 1)], r0[(j + q + 1) & (H - 1)]);
               }
               const Pair<T> b2 = pair_fma_s(nl1, c2, pair_make(r1[j + q], r1[j + q + 1]));
               pair_get(b2, r1[j + q], r1[j + q + 1]);
-            } else {
-              if (j + q + 1 > k) {
-                if (j < H && k < H) r0[j < H ? j + q + 1 : 1] = fma_(nl0, c[q + 1], r0[j < H ? j + q + 1 : 1]);
-                r1[j + q + 1] = fma_(nl1, c[q + 1], r1[j + q + 1]);
-              }
+            } else if (j + q + 1 > k) {
+              if (j + q + 1 < H) r0[(j + q + 1) & (H - 1)] = fma_(nl0, c[q + 1], r0[(j + q + 1) & (H - 1)]);
+              r1[j + q + 1] = fma_(nl1, c[q + 1], r1[j + q + 1]);
+            }
+          }
+        }
+      }
+    }
+    // columns 32..63: pivot in row k - 32 of the second row set, which alone is still open
+#pragma unroll
+    for (int k = H; k < D; ++k) {
+      if (PADDED || k < n) {
+        const T akk = __shfl_sync(0xffffffffu, r1[k], k - H);
+        T lkk, inv;
+        pivot_<T>(akk, lkk, inv);
+        T* cb = colbuf + (k & 1) * D;
+        const T l1 = (lane == k - H) ? lkk : r1[k] * inv;
+        r1[k] = l1;
+        cb[lane + H] = l1;
+        if (lane == k - H) { dg[k] = lkk; dginv[k] = inv; }
+        __syncwarp();
+        const T nl1 = -l1;
+#pragma unroll
+        for (int j = ((k + 1) / V) * V; j < D; j += V) {
+          T c[V];
+          ldv<T, V>(c, cb + j);
+#pragma unroll
+          for (int q = 0; q < V; q += 2) {
+            if (j + q > k) {
+              const Pair<T> b2 = pair_fma_s(nl1, pair_make(c[q], c[q + 1]), pair_make(r1[j + q], r1[j + q + 1]));
+              pair_get(b2, r1[j + q], r1[j + q + 1]);
+            } else if (j + q + 1 > k) {
+              r1[j + q + 1] = fma_(nl1, c[q + 1], r1[j + q + 1]);
             }
           }
         }
