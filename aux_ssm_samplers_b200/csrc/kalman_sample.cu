@@ -167,7 +167,7 @@ template <typename T, int D> __device__ __forceinline__ void store_rows_pairs(T*
 // instruction cache: warps that drift apart each stream it from L2 (ncu: `no_instruction` was the largest stall).
 // Seven warps per CTA, re-aligned by one block barrier per item, fetch every line once for all seven.
 template <typename T, int D, bool LEAN> struct ElemCfg {
-  static constexpr int W = (LEAN && D <= 32) ? 7 : 1;
+  static constexpr int W = (LEAN && D <= 32) ? 7 : 1;  // (four D = 64 items per CTA were measured: no gain)
   static constexpr int MINB = (Occ<T, D>::MINB / W) > 0 ? Occ<T, D>::MINB / W : 1;
 };
 

@@ -35,8 +35,12 @@ template <typename T, int D> struct Occ {
   static constexpr int MINB = (D <= 32) ? (sizeof(T) == 4 ? 512 : 256) / Tile<D>::NT : 1;
 };
 
+// Barrier over the Tile<D>::NT threads of ONE work item.  Items are laid out along threadIdx.y when a CTA hosts
+// several of them (sampler elements kernel), so multi-warp items use the named barrier 1 + threadIdx.y; with one
+// item per CTA that is simply a block barrier.
 template <int D> __device__ __forceinline__ void cta_sync() {
-  if (Tile<D>::NT == 32) __syncwarp(); else __syncthreads();
+  if (Tile<D>::NT == 32) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)threadIdx.y), "n"(Tile<D>::NT) : "memory");
 }
 
 template <typename T, int N> struct alignas((sizeof(T) * N > 16) ? 16 : sizeof(T) * N) Vec { T v[N]; };
@@ -531,7 +535,7 @@ template <int D> struct CholWs { static constexpr int WORDS = 4 * D; };
 template <typename T, bool PADDED = false>
 __device__ __forceinline__ void chol_reg64(T* A, T* dg, T* dginv, T* colbuf, int n) {
   constexpr int D = 64, H = 32, LD = Tile<D>::LD, V = 4;
-  __syncthreads();
+  cta_sync<64>();
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     T r0[H], r1[D];
@@ -627,7 +631,7 @@ __device__ __forceinline__ void chol_reg64(T* A, T* dg, T* dginv, T* colbuf, int
       if (PADDED || lane + H < n) stv<T, V>(A + (lane + H) * LD + j, t1);
     }
   }
-  __syncthreads();
+  cta_sync<64>();
 }
 
 // In-place lower Cholesky of the n x n block; strict upper triangle zeroed; non-PD pivots give NaN.
