@@ -44,7 +44,10 @@ def _nvcc():
 def _compile_one(nvcc, src, headers):
     obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
     stamp_file = obj + ".stamp"
-    stamp = _stamp([os.path.join(CSRC, src)] + headers)
+    deps = [os.path.join(CSRC, src)] + headers
+    if src.endswith("_f64.cu"):  # X_f64.cu is "#define AUXSSM_ONLY_F64 / #include X.cu"
+        deps.append(os.path.join(CSRC, src[:-7] + ".cu"))
+    stamp = _stamp(deps)
     if os.path.exists(obj) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return obj, False
     cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
@@ -66,6 +69,10 @@ def build_library(verbose=False, force=False):
         for f in os.listdir(OBJ_DIR):
             os.remove(os.path.join(OBJ_DIR, f))
     srcs = _sources()
+    # the slowest translation units first, so that they overlap with everything else on the worker pool
+    heavy = ["kalman_filter.cu", "kalman_filter_f64.cu", "kalman_sample.cu", "kalman_sample_f64.cu", "lgssm_logpdf.cu",
+             "lgssm_logpdf_f64.cu", "csmc_guided.cu", "csmc_independent.cu", "csmc_bootstrap.cu"]
+    srcs = [h for h in heavy if h in srcs] + [x for x in srcs if x not in heavy]
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         results = list(ex.map(lambda s: _compile_one(nvcc, s, headers), srcs))
     objs = [o for o, _ in results]

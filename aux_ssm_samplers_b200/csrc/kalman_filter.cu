@@ -1155,6 +1155,10 @@ static int filter_entry(void* stream, const auxssm_lgssm_desc* d, const T* ys, c
 
 }  // namespace auxssm
 
+// This translation unit carries the fp32 entry point (and the dtype-independent scratch query); the fp64
+// instantiations are compiled by kalman_filter_f64.cu, which includes this file with AUXSSM_ONLY_F64 defined, so
+// that the two halves build in parallel.
+#ifndef AUXSSM_ONLY_F64
 extern "C" __attribute__((visibility("default"))) size_t auxssm_kalman_filter_scratch_bytes(const auxssm_lgssm_desc* desc, int32_t elem_size) {
   if (auxssm::check_desc(desc, "auxssm_kalman_filter_scratch_bytes")) return 0;
   return auxssm::make_plan(desc, (size_t)elem_size).total;
@@ -1167,6 +1171,7 @@ extern "C" __attribute__((visibility("default"))) int32_t auxssm_kalman_filter_f
   return auxssm::filter_entry<float>(stream, desc, ys, m0, P0, Fs, Qs, bs, Hs, Rs, cs, ms, Ps, ell, scratch,
                                      scratch_bytes);
 }
+#else
 extern "C" __attribute__((visibility("default"))) int32_t auxssm_kalman_filter_f64(void* stream, const auxssm_lgssm_desc* desc, const double* ys,
                                             const double* m0, const double* P0, const double* Fs, const double* Qs,
                                             const double* bs, const double* Hs, const double* Rs, const double* cs,
@@ -1175,3 +1180,4 @@ extern "C" __attribute__((visibility("default"))) int32_t auxssm_kalman_filter_f
   return auxssm::filter_entry<double>(stream, desc, ys, m0, P0, Fs, Qs, bs, Hs, Rs, cs, ms, Ps, ell, scratch,
                                       scratch_bytes);
 }
+#endif

@@ -456,6 +456,10 @@ static int sample_entry(void* stream, const auxssm_lgssm_desc* d, const T* ms, c
 
 }  // namespace auxssm
 
+// This translation unit carries the fp32 entry point (and the dtype-independent scratch query); the fp64
+// instantiations are compiled by kalman_sample_f64.cu, which includes this file with AUXSSM_ONLY_F64 defined, so
+// that the two halves build in parallel.
+#ifndef AUXSSM_ONLY_F64
 extern "C" __attribute__((visibility("default"))) size_t auxssm_kalman_sample_scratch_bytes(const auxssm_lgssm_desc* desc, int32_t elem_size) {
   if (auxssm::check_desc(desc, "auxssm_kalman_sample_scratch_bytes")) return 0;
   return auxssm::make_sample_plan(desc, (size_t)elem_size).total;
@@ -465,8 +469,10 @@ extern "C" __attribute__((visibility("default"))) int32_t auxssm_kalman_sample_f
                                             const float* eps, float* xs, void* scratch, size_t scratch_bytes) {
   return auxssm::sample_entry<float>(stream, desc, ms, Ps, Fs, Qs, bs, eps, xs, scratch, scratch_bytes);
 }
+#else
 extern "C" __attribute__((visibility("default"))) int32_t auxssm_kalman_sample_f64(void* stream, const auxssm_lgssm_desc* desc, const double* ms,
                                             const double* Ps, const double* Fs, const double* Qs, const double* bs,
                                             const double* eps, double* xs, void* scratch, size_t scratch_bytes) {
   return auxssm::sample_entry<double>(stream, desc, ms, Ps, Fs, Qs, bs, eps, xs, scratch, scratch_bytes);
 }
+#endif

@@ -433,6 +433,10 @@ static int logpdf_entry(void* stream, const auxssm_lgssm_desc* d, uint32_t which
 
 }  // namespace auxssm
 
+// This translation unit carries the fp32 entry point (and the dtype-independent scratch query); the fp64
+// instantiations are compiled by lgssm_logpdf_f64.cu, which includes this file with AUXSSM_ONLY_F64 defined, so
+// that the two halves build in parallel.
+#ifndef AUXSSM_ONLY_F64
 extern "C" __attribute__((visibility("default"))) size_t auxssm_lgssm_logpdf_scratch_bytes(const auxssm_lgssm_desc* desc, int32_t elem_size) {
   if (auxssm::check_desc(desc, "auxssm_lgssm_logpdf_scratch_bytes")) return 0;
   const size_t a = auxssm::make_logpdf_plan(desc, (size_t)elem_size, AUXSSM_LOGPDF_POSTERIOR).total;
@@ -448,6 +452,7 @@ extern "C" __attribute__((visibility("default"))) int32_t auxssm_lgssm_logpdf_f3
   return auxssm::logpdf_entry<float>(stream, desc, which, ys, xs, ell, m0, P0, Fs, Qs, bs, Hs, Rs, cs, out, scratch,
                                      scratch_bytes);
 }
+#else
 extern "C" __attribute__((visibility("default"))) int32_t auxssm_lgssm_logpdf_f64(void* stream, const auxssm_lgssm_desc* desc, uint32_t which,
                                            const double* ys, const double* xs, const double* ell, const double* m0,
                                            const double* P0, const double* Fs, const double* Qs, const double* bs,
@@ -456,3 +461,4 @@ extern "C" __attribute__((visibility("default"))) int32_t auxssm_lgssm_logpdf_f6
   return auxssm::logpdf_entry<double>(stream, desc, which, ys, xs, ell, m0, P0, Fs, Qs, bs, Hs, Rs, cs, out, scratch,
                                       scratch_bytes);
 }
+#endif
