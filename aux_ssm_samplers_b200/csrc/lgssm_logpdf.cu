@@ -234,19 +234,24 @@ __global__ void __launch_bounds__(NTB) logpdf_fast_kernel(LogpdfFastArgs<T> fa) 
 #pragma unroll
       for (int i = 0; i < D; ++i) z[i] = (i < dx) ? xp[i] : T(0);  // z <- x_{t-1}
       T r[D];
+      if (a.d.flags & AUXSSM_FLAG_F_IS_DIAGONAL) {  // promise of the caller: F x is one multiply per entry
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        T acc0 = sb[i], acc1 = T(0);
+        for (int i = 0; i < D; ++i) r[i] = x[i] - fma_(sF[i * D + i], z[i], sb[i]);
+      } else {
 #pragma unroll
-        for (int k = 0; k < D; k += V) {
-          T f[V];
-          ldv<T, V>(f, sF + i * D + k);
+        for (int i = 0; i < D; ++i) {
+          T acc0 = sb[i], acc1 = T(0);
 #pragma unroll
-          for (int q = 0; q < V; ++q) {
-            if ((q & 1) == 0) acc0 = fma_(f[q], z[k + q], acc0); else acc1 = fma_(f[q], z[k + q], acc1);
+          for (int k = 0; k < D; k += V) {
+            T f[V];
+            ldv<T, V>(f, sF + i * D + k);
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+              if ((q & 1) == 0) acc0 = fma_(f[q], z[k + q], acc0); else acc1 = fma_(f[q], z[k + q], acc1);
+            }
           }
+          r[i] = x[i] - (acc0 + acc1);
         }
-        r[i] = x[i] - (acc0 + acc1);
       }
       T quad = T(0);
 #pragma unroll

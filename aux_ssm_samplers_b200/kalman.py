@@ -248,7 +248,7 @@ def sampling(key, ms, Ps, lgssm, parallel, *, inner_batch=False, time_chunks=0, 
     return xs
 
 
-def _logpdf(which, ys, xs, ell, lgssm, inner_batch):
+def _logpdf(which, ys, xs, ell, lgssm, inner_batch, f_diagonal=False):
     lgssm = LGSSM(*lgssm)
     dev = _lib.require_cuda(xs)
     dtype = xs.dtype
@@ -256,7 +256,7 @@ def _logpdf(which, ys, xs, ell, lgssm, inner_batch):
     dims = _infer_dims(ys, lgssm.m0, inner_batch, xs=xs)
     dims = dims._replace(dx=xs.shape[-1])
     hid = lgssm.Hs is None
-    d = _fill_desc(dims, False, 0, hid, isinstance(lgssm.Rs, Diagonal))
+    d = _fill_desc(dims, False, 0, hid, isinstance(lgssm.Rs, Diagonal), f_diagonal)
     p = _prep_lgssm(d, dims, lgssm, dtype)
     ysc = None
     if ys is not None:
@@ -277,15 +277,15 @@ def _logpdf(which, ys, xs, ell, lgssm, inner_batch):
     return out if dims.has_chain else out[0]
 
 
-def posterior_logpdf(ys, xs, ell, lgssm, *, inner_batch=False):
-    """log p(xs | ys) of a trajectory (base.py:73-96)."""
-    return _logpdf(_lib.LOGPDF_POSTERIOR, ys, xs, ell, lgssm, inner_batch)
+def posterior_logpdf(ys, xs, ell, lgssm, *, inner_batch=False, f_diagonal=False):
+    """log p(xs | ys) of a trajectory (base.py:73-96).  ``f_diagonal``: same promise as in ``filtering``."""
+    return _logpdf(_lib.LOGPDF_POSTERIOR, ys, xs, ell, lgssm, inner_batch, f_diagonal)
 
 
-def prior_logpdf(xs, lgssm, *, inner_batch=False):
+def prior_logpdf(xs, lgssm, *, inner_batch=False, f_diagonal=False):
     """log p(xs) (base.py:100-134)."""
     lg = LGSSM(*lgssm)
-    return _logpdf(_lib.LOGPDF_PRIOR, None, xs, None, lg._replace(Hs=None, Rs=None, cs=None), inner_batch)
+    return _logpdf(_lib.LOGPDF_PRIOR, None, xs, None, lg._replace(Hs=None, Rs=None, cs=None), inner_batch, f_diagonal)
 
 
 def log_likelihood(ys, xs, lgssm, *, inner_batch=False):
@@ -357,7 +357,7 @@ def get_kernel(dynamics_factory, observations_factory, log_likelihood_fn, parall
         if x_prop is None:
             x_prop = sampling(sampling_key, ms, Ps, lgssm, parallel, time_chunks=time_chunks,
                               f_diagonal=f_diagonal)
-        log_lgssm = posterior_logpdf(ys, x_prop, ell, lgssm)
+        log_lgssm = posterior_logpdf(ys, x_prop, ell, lgssm, f_diagonal=f_diagonal)
         return log_lgssm, log_likelihood_fn(x_prop), x_prop
 
     def kernel(key, state, delta):
