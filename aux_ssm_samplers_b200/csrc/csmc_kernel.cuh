@@ -254,7 +254,12 @@ __device__ __forceinline__ T propose_and_weight(const auxssm_csmc_desc& dsc, con
 #pragma unroll
     for (int i = 0; i < D; ++i) xn[i] = pinned ? m.xs_t[i] : m.mean_t[i] + m.s_t * eps[i];
     T lw = prior_logpdf<T, D>(m, first, xn, xpred) + potential<T, D>(dsc, m.y, xn);
-    if (dsc.gradient) lw += iso_logpdf<T, D>(xn, m.u_t, m.s_t, dsc.d) - iso_logpdf<T, D>(xn, m.mean_t, m.s_t, dsc.d);
+    // gradient == 1 follows the reference to the letter: GradientAuxiliaryG0 (independent.py:173-190) corrects every
+    // particle, GradientAuxiliaryGt (:252-268) sums its correction over ALL particles (no axis=-1), i.e. adds a
+    // per-step constant that cancels in every normalisation -- omitted here.  gradient == 2 applies the per-particle
+    // correction at every step (the importance weight the proposal calls for).
+    if (dsc.gradient == 2 || (dsc.gradient == 1 && first))
+      lw += iso_logpdf<T, D>(xn, m.u_t, m.s_t, dsc.d) - iso_logpdf<T, D>(xn, m.mean_t, m.s_t, dsc.d);
     return lw;
   } else {
     // GUIDED: mu = xpred + K (u - xpred); x = mu + cL eps

@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
           for (int ct = 0; ct < CT; ++ct) q2 += zq[ct * NPAD + i];
           lw += T(-0.5) * q2 + (first ? cst_p0 : cst_q);
         }
-        if (PROP == AUXSSM_PROP_INDEPENDENT && dsc.gradient) lw += T(-0.5) * (su - sm);
+        if (PROP == AUXSSM_PROP_INDEPENDENT && (dsc.gradient == 2 || (dsc.gradient == 1 && first))) lw += T(-0.5) * (su - sm);  // see csmc_kernel.cuh
         if (PROP == AUXSSM_PROP_GUIDED) {
           lw += T(-0.5) * su - T(d) * (log(s_c) + log_2pi_half<T>());
           lw -= ((i == 0) ? pin : T(-0.5) * qe) + cst_l;

@@ -179,6 +179,10 @@ int32_t auxssm_sv_log_potential_f64(void* stream, int64_t n_chains, int64_t n_pe
  *   proposal   BOOTSTRAP    propose from the prior, weight = potential
  *              INDEPENDENT  N(u_t + s_t^2 grad_t, s_t^2 I), weight = log prior transition + potential
  *                           (+ log N(x;u,s) - log N(x;mean,s) when `gradient`)      independent.py:144-268
+ *                           gradient = 1 is the reference to the letter: per-particle correction at t = 0
+ *                           (GradientAuxiliaryG0 :173-190); for t >= 1 GradientAuxiliaryGt (:252-268) sums the
+ *                           correction over all particles, a per-step constant that cancels in every normalisation
+ *                           and is therefore not added.  gradient = 2 corrects every particle at every step.
  *              GUIDED       N(mu_t, Lambda_t), mu_t = xpred + K_t (u_t - xpred); K_t, chol Lambda_t from
  *                           auxssm_guided_gains_*                        auxiliary_guided_csmc.py:90-167
  * Anything else must use the unfused primitives below, one call per time step.
@@ -198,7 +202,7 @@ typedef struct auxssm_csmc_desc {
   int32_t T, N, d, n_chains;
   int32_t proposal, potential, resampling;
   int32_t backward;         /* 0: ancestor tracing; 1: backward sampling with Pt = the prior transition */
-  int32_t gradient;         /* INDEPENDENT only: weights carry the gradient correction                   */
+  int32_t gradient;         /* INDEPENDENT only: 0 none, 1 reference semantics, 2 per-particle at every step (above) */
   int64_t ys_chain_stride;  /* 0: one data set ys[T,d] shared by all chains; T*d: one per chain          */
   int64_t gains_time_stride;/* GUIDED: d*d if K / cholLam are [T,d,d], 0 if time-invariant [d,d]         */
   double sig;               /* GAUSSIAN potential: observation std                                       */

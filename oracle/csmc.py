@@ -36,7 +36,7 @@ csmc/generic.py, csmc/independent.py and the backward-sampling index sequence ar
 """
 import numpy as np
 
-from .linalg import LOG_2PI, chol, mv, mvn_logpdf, norm_logpdf, solve_lower
+from .linalg import LOG_2PI, chol, cho_solve, mv, mvn_logpdf, norm_logpdf, solve_lower
 
 # --------------------------------------------------------------------------------------------
 # canonical reductions (shared with the CUDA kernels)
@@ -236,6 +236,25 @@ class LinearGaussianModel:
         raise ValueError(self.potential)
 
 
+def grad_log_target(model, u):
+    """Gradient at ``u`` [T, d] of ``_log_pdf`` (csmc/independent.py:121-137): log M0(u_0) + G0(u_0) +
+    sum_t [Gt(u_t) + log Mt(u_t | u_{t-1})], which the reference obtains with ``jax.grad``; analytic here for the
+    closed family set (linear-Gaussian prior; flat / Gaussian / SV potential)."""
+    u = np.asarray(u, dtype=model.dtype)
+    r0 = cho_solve(model.cP0, u[0] - model.m0)
+    res = u[1:] - (mv(model.F, u[:-1]) + model.b)
+    rt = cho_solve(model.cQ, res.T).T  # one solve per time step
+    g = np.zeros_like(u)
+    g[0] -= r0
+    g[1:] -= rt
+    g[:-1] += rt @ model.F
+    if model.potential == "gaussian":
+        g += (model.ys - u) / model.sig ** 2
+    elif model.potential == "sv":
+        g += 0.5 * model.ys ** 2 * np.exp(-u) - 0.5
+    return g
+
+
 class BootstrapFK:
     """Bootstrap Feynman--Kac model: propose from the prior, weight by the potential."""
 
@@ -262,12 +281,19 @@ class IndependentAuxFK:
     G0' = G0 + log M0;  Gt' = log Mt(x_t | x_{t-1}) + Gt;  with ``gradient`` the weights also carry
     log N(x; u, s) - log N(x; mean, s) (GradientAuxiliaryG0/Gt, :173-190, :252-268).
     ``grad`` is the gradient of the log target at u (zeros when gradient=False).
+
+    ``gradient=True`` (or 1) is the reference to the letter: ``GradientAuxiliaryG0`` corrects every particle, while
+    ``GradientAuxiliaryGt.__call__`` (independent.py:262-266) calls ``jnp.sum`` WITHOUT ``axis=-1``: its correction
+    is summed over all particles, i.e. one constant per time step, which cancels in every ``normalize`` and in the
+    backward weights -- it is left out here (log-weight histories differ from the reference's by that constant).
+    ``gradient=2`` applies the per-particle correction at every step (what the proposal's importance weight calls
+    for; not what the reference computes).  Pinned by tests/golden/ref_csmc.npz (ind_g1_*).
     """
 
     def __init__(self, model, u, sqrt_half_delta, grad=None, gradient=False):
         self.m, self.u, self.s = model, u, np.asarray(sqrt_half_delta, dtype=model.dtype)
         self.grad = np.zeros_like(u) if grad is None else grad
-        self.gradient = gradient
+        self.gradient = int(gradient)
 
     def _mean(self, t):
         return self.u[t] + self.s[t] ** 2 * self.grad[t]
@@ -279,7 +305,7 @@ class IndependentAuxFK:
         return self._mean(t) + self.s[t] * eps
 
     def _corr(self, t, x):
-        if not self.gradient:
+        if not self.gradient or (self.gradient == 1 and t > 0):
             return 0.0
         return (np.sum(norm_logpdf(x, self.u[t], self.s[t]), axis=-1)
                 - np.sum(norm_logpdf(x, self._mean(t), self.s[t]), axis=-1))

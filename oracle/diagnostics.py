@@ -41,10 +41,13 @@ def effective_sample_size(x, var=None):
     mask0 = (rho_even + rho_odd) > 0.0
     mask = np.logical_and.accumulate(mask0)
     max_t = int(np.max(np.flatnonzero(mask))) if mask.any() else 0
+    # ess.py:126-131: `mask.at[max_t + 1].set(rho_even[max_t + 1] > 0)`; when max_t + 1 == k the scatter is OUT OF
+    # BOUNDS and XLA drops it, whereas the two gathers (`rho_hat_even[indices]`, ess.py:131 and :156) clamp.
     idx = min(max_t + 1, k - 1)
     rho_odd = np.where(mask, rho_odd, 0.0)
     mask_even = mask.copy()
-    mask_even[idx] = rho_even[idx] > 0
+    if max_t + 1 < k:
+        mask_even[max_t + 1] = rho_even[max_t + 1] > 0
     rho_even = np.where(mask_even, rho_even, 0.0)
     s = rho_even + rho_odd
     even_f, odd_f = rho_even.copy(), rho_odd.copy()
@@ -58,3 +61,9 @@ def effective_sample_size(x, var=None):
     tau = -1.0 + 2.0 * np.sum(even_f + odd_f) - even_f[idx]
     tau = max(tau, 1.0 / np.log10(ess_raw))
     return float(ess_raw / tau)
+
+
+def delta_adaptation(delta, target_rate, acceptance_rate, adaptation_rate, min_delta=1e-20, max_delta=1e20):
+    """Reference ``aux_samplers/common.py:4-32``: delta * exp(rate (acc - target)), clipped."""
+    rate = np.exp(adaptation_rate * (np.asarray(acceptance_rate) - target_rate))
+    return np.clip(np.asarray(delta) * rate, min_delta, max_delta)
