@@ -43,15 +43,17 @@ class CsmcDesc(ctypes.Structure):
         ("proposal", ctypes.c_int32), ("potential", ctypes.c_int32), ("resampling", ctypes.c_int32),
         ("backward", ctypes.c_int32), ("gradient", ctypes.c_int32),
         ("ys_chain_stride", ctypes.c_int64), ("gains_time_stride", ctypes.c_int64), ("sig", ctypes.c_double),
+        ("rng_seed", ctypes.c_uint64), ("rng_counter", ctypes.c_uint64), ("rng_counter_ptr", ctypes.c_void_p),
     ]
 
 
 PROP_BOOTSTRAP, PROP_INDEPENDENT, PROP_GUIDED = 0, 1, 2
 POT_FLAT, POT_GAUSSIAN, POT_SV = 0, 1, 2
-RESAMPLE_MULTINOMIAL, RESAMPLE_KILLING = 0, 1
+RESAMPLE_MULTINOMIAL, RESAMPLE_KILLING, RESAMPLE_SYSTEMATIC = 0, 1, 2
 
 _P = ctypes.c_void_p
 _I32, _I64, _U32, _SZ = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_size_t
+_U64, _F64 = ctypes.c_uint64, ctypes.c_double
 _DESC = ctypes.POINTER(LgssmDesc)
 
 # name -> (restype, argtypes); `{s}` expands to f32 / f64
@@ -59,6 +61,7 @@ _SIGNATURES = {
     "auxssm_last_error": (ctypes.c_char_p, []),
     "auxssm_version": (_I32, []),
     "auxssm_launch_count": (ctypes.c_int64, []),
+    "auxssm_dispatch_log": (ctypes.c_char_p, [_I32]),
     "auxssm_kalman_filter_scratch_bytes": (_SZ, [_DESC, _I32]),
     "auxssm_kalman_filter_{s}": (_I32, [_P, _DESC] + [_P] * 12 + [_P, _SZ]),
     "auxssm_kalman_sample_scratch_bytes": (_SZ, [_DESC, _I32]),
@@ -76,6 +79,15 @@ _SIGNATURES = {
     "auxssm_resample_multinomial_{s}": (_I32, [_P, _I64, _I32, _P, _P, _P]),
     "auxssm_resample_killing_{s}": (_I32, [_P, _I64, _I32, _P, _P, _P, _P]),
     "auxssm_categorical_{s}": (_I32, [_P, _I64, _I32, _P, _P, _P]),
+    "auxssm_resample_systematic_{s}": (_I32, [_P, _I64, _I32, _I32, _P, _P, _P]),
+    "auxssm_csmc_grad_log_target_{s}": (_I32, [_P, ctypes.POINTER(CsmcDesc)] + [_P] * 8),
+    "auxssm_cholesky_{s}": (_I32, [_P, _I64, _I32, _P, _P]),
+    "auxssm_delta_adaptation_{s}": (_I32, [_P, _I64, _P, _P, _I32, _F64, _F64, _F64, _F64, _P]),
+    "auxssm_mcmc_stats_{s}": (_I32, [_P, _I32, _I64, _I32, _P, _P, _P, _F64, _P]),
+    "auxssm_autocov_{s}": (_I32, [_P, _I32, _I64, _P, _P, _P]),
+    "auxssm_philox_uniform_{s}": (_I32, [_P, _U64, _P, _I64, _P]),
+    "auxssm_philox_normal_{s}": (_I32, [_P, _U64, _P, _I64, _P]),
+    "auxssm_philox_advance": (_I32, [_P, _P, _U64]),
 }
 
 
@@ -176,6 +188,11 @@ def call(name, *args):
 def launch_count():
     """Cumulative number of CUDA kernels libauxssm.so has launched in this process."""
     return int(lib().auxssm_launch_count())
+
+
+def dispatch_log(reset=True):
+    """Names of the kernels this host thread has launched since the last reset (which path served a call)."""
+    return lib().auxssm_dispatch_log(1 if reset else 0).decode("utf-8", "replace").split(";")
 
 
 def stream_ptr(device):

@@ -38,6 +38,18 @@ class CSMCState(NamedTuple):
     updated: torch.Tensor
 
 
+def cholesky(A):
+    """Lower Cholesky factors of ``A[..., d, d]`` computed by libauxssm (``auxssm_cholesky_*``): an all-NaN factor
+    where the factorisation fails (``jnp.linalg.cholesky``), a plain square root when ``d == 1``."""
+    dev = _lib.require_cuda(A)
+    Ac = A.contiguous()
+    L = torch.empty_like(Ac)
+    d = A.shape[-1]
+    _lib.call("auxssm_cholesky_" + _lib.suffix(A.dtype), _lib.stream_ptr(dev), Ac.numel() // (d * d), d, _lib.ptr(Ac),
+              _lib.ptr(L))
+    return L
+
+
 # ---- model-family descriptors (mirroring csmc/base.py's abstract classes) -------------------------
 
 class Distribution:
@@ -61,7 +73,7 @@ class GaussianDistribution(Distribution, UnivariatePotential):
 
     def __init__(self, m0, P0):
         self.m0, self.P0 = m0, P0
-        self.chol_P0 = (torch.linalg.cholesky(P0) if P0.shape[-1] > 1 else torch.sqrt(P0)).contiguous()
+        self.chol_P0 = cholesky(P0)  # auxssm_cholesky_* (jnp.linalg.cholesky semantics; sqrt when d = 1)
 
     def logpdf(self, x):  # presence of this attribute is what the reference checks (csmc.py:49)
         raise NotImplementedError("evaluated inside the fused kernel")
@@ -73,7 +85,7 @@ class LinearGaussianDynamics(Dynamics):
 
     def __init__(self, F, Q, b):
         self.F, self.Q, self.b = F, Q, b
-        self.chol_Q = (torch.linalg.cholesky(Q) if Q.shape[-1] > 1 else torch.sqrt(Q)).contiguous()
+        self.chol_Q = cholesky(Q)
 
     def logpdf(self, x_t_p_1, x_t, params):
         raise NotImplementedError("evaluated inside the fused kernel")
@@ -149,23 +161,39 @@ def _sweep(x_star, M0, Mt, pot, N, backward, resampling, key, aux=None, return_h
     desc.T, desc.N, desc.d, desc.n_chains = T, N, d, C
     desc.proposal = aux.proposal if aux is not None else _lib.PROP_BOOTSTRAP
     desc.potential = pot.kind
-    desc.resampling = {"multinomial": _lib.RESAMPLE_MULTINOMIAL, "killing": _lib.RESAMPLE_KILLING}[resampling]
+    desc.resampling = {"multinomial": _lib.RESAMPLE_MULTINOMIAL, "killing": _lib.RESAMPLE_KILLING,
+                       "systematic": _lib.RESAMPLE_SYSTEMATIC}[resampling]
     desc.backward = 1 if backward else 0
-    desc.gradient = 1 if (aux is not None and aux.gradient) else 0
+    desc.gradient = int(aux.gradient) if aux is not None else 0
     desc.sig = float(pot.sig)
+
+    def cvt(t):
+        if t is None:
+            return None
+        _lib.require_cuda(x, t)
+        return t.to(dtype=dtype).contiguous()
+
     ys = None
     if pot.ys is not None:
-        ys = pot.ys.to(dtype).contiguous()
+        ys = cvt(pot.ys)
         desc.ys_chain_stride = 0 if ys.dim() == 2 else T * d
-    cvt = lambda t: None if t is None else t.to(device=dev, dtype=dtype).contiguous()
     u = shd = grad = K = cL = None
     if aux is not None:
         u, shd, grad, K, cL = cvt(aux.u), cvt(aux.sqrt_half_delta), cvt(aux.grad), cvt(aux.K), cvt(aux.chol_Lam)
         desc.gains_time_stride = 0 if (K is None or K.dim() == 2) else d * d
-    normals = key.normal((C, T, N, d), dtype, dev).contiguous()
-    u_res = key.uniform((C, max(T - 1, 0), N), dtype, dev).contiguous()
-    u_kill = key.uniform((C, max(T - 1, 0), N), dtype, dev).contiguous() if resampling == "killing" else None
-    u_bwd = key.uniform((C, T), dtype, dev).contiguous()
+    in_kernel = bool(getattr(key, "in_kernel", False)) and hasattr(key, "counter")
+    if in_kernel:
+        # counter-based draws generated inside the sweep (include/auxssm.h: rng_seed / rng_counter_ptr): the
+        # [C,T,N,d] normals and [C,T-1,N] uniforms never exist in HBM
+        normals = u_res = u_kill = u_bwd = None
+        desc.rng_seed = key.seed
+        desc.rng_counter_ptr = key.counter.data_ptr()
+    else:
+        normals = key.normal((C, T, N, d), dtype, dev).contiguous()
+        # systematic resampling consumes the three uniforms (U, V, W) of resamplings.py:65 per step
+        u_res = key.uniform((C, max(T - 1, 0), 3 if resampling == "systematic" else N), dtype, dev).contiguous()
+        u_kill = key.uniform((C, max(T - 1, 0), N), dtype, dev).contiguous() if resampling == "killing" else None
+        u_bwd = key.uniform((C, T), dtype, dev).contiguous()
     x_out = torch.empty_like(x)
     anc = torch.empty((C, T), dtype=torch.int32, device=dev)
     xs_h = lw_h = a_h = None
@@ -186,6 +214,8 @@ def _sweep(x_star, M0, Mt, pot, N, backward, resampling, key, aux=None, return_h
               _lib.ptr(ys), _lib.ptr(u), _lib.ptr(shd), _lib.ptr(grad), _lib.ptr(K), _lib.ptr(cL),
               _lib.ptr(normals), _lib.ptr(u_res), _lib.ptr(u_kill), _lib.ptr(u_bwd), _lib.ptr(x_out), _lib.ptr(anc),
               _lib.ptr(xs_h), _lib.ptr(lw_h), _lib.ptr(a_h), _lib.ptr(scratch), int(nbytes))
+    if in_kernel:
+        key.advance(4 if resampling == "killing" else 3)
     updated = anc != 0
     if squeeze:
         x_out, updated, anc = x_out[0], updated[0], anc[0]
@@ -223,10 +253,12 @@ def _aux_u(key, x, delta):
     C, T, d = x.shape
     dl = torch.as_tensor(delta, dtype=x.dtype, device=x.device)
     dl = dl.expand(T) if dl.dim() == 0 else dl
-    dl = dl.expand(C, T).contiguous() if dl.dim() == 1 else dl.contiguous()
+    shared = dl.dim() == 1
+    dl2 = dl.expand(C, T) if shared else dl
     eps = key.normal((C, T, d), x.dtype, x.device)
-    u = auxiliary_draw(x.reshape(C * T, d), eps.reshape(C * T, d), dl.reshape(C * T)).reshape(C, T, d)
-    return u, torch.sqrt(0.5 * dl)
+    u = auxiliary_draw(x.reshape(C * T, d), eps.reshape(C * T, d), dl2.reshape(C * T)).reshape(C, T, d)
+    shd = torch.sqrt(0.5 * dl)
+    return u, (shd.expand(C, T) if shared else shd)  # shared schedule: stride-0 chain axis (see guided_factory)
 
 
 def get_generic_kernel(factory, N, backward=False, Pt=None, *, resampling="multinomial", return_history=False):
@@ -268,38 +300,48 @@ def get_generic_kernel(factory, N, backward=False, Pt=None, *, resampling="multi
 def grad_log_target(u, M0, G0, Mt, Gt):
     """Gradient at ``u`` [C,T,d] of log M0(u_0) + G0(u_0) + sum_t (Gt(u_t) + log Mt(u_t | u_{t-1})), the quantity
     the reference obtains with ``jax.grad(_log_pdf)`` (independent.py:62,121-137); analytic for the closed
-    family set.  Host-side proposal construction (torch), not part of the fused sweep."""
+    family set, computed by ``auxssm_csmc_grad_log_target_*`` (one thread per (chain, time step))."""
     pot = _check_family(M0, G0, Mt, Gt)
-    F, b = Mt.F.to(u), Mt.b.to(u)
-    r0 = torch.cholesky_solve((u[:, 0] - M0.m0.to(u)).unsqueeze(-1), M0.chol_P0.to(u)).squeeze(-1)
-    res = u[:, 1:] - (u[:, :-1] @ F.T + b)
-    rt = torch.cholesky_solve(res.unsqueeze(-1), Mt.chol_Q.to(u)).squeeze(-1)
-    grad = torch.zeros_like(u)
-    grad[:, 0] -= r0
-    grad[:, 1:] -= rt
-    grad[:, :-1] += rt @ F
-    if pot.kind == _lib.POT_GAUSSIAN:
-        grad += (pot.ys.to(u) - u) / pot.sig ** 2
-    elif pot.kind == _lib.POT_SV:
-        y = pot.ys.to(u)
-        grad += 0.5 * y * y * torch.exp(-u) - 0.5
+    dev = _lib.require_cuda(u)
+    dtype = u.dtype
+    u = u.contiguous()
+    C, T, d = u.shape
+    desc = CsmcDesc()
+    desc.T, desc.N, desc.d, desc.n_chains = T, 1, d, C
+    desc.potential, desc.sig = pot.kind, float(pot.sig)
+    cvt = lambda t: t.to(dtype=dtype).contiguous() if _lib.require_cuda(u, t) else None
+    ys = None
+    if pot.ys is not None:
+        ys = cvt(pot.ys)
+        desc.ys_chain_stride = 0 if ys.dim() == 2 else T * d
+    m0_, lp0_, f_, b_, lq_ = cvt(M0.m0), cvt(M0.chol_P0), cvt(Mt.F), cvt(Mt.b), cvt(Mt.chol_Q)
+    grad = torch.empty_like(u)
+    _lib.call("auxssm_csmc_grad_log_target_" + _lib.suffix(dtype), _lib.stream_ptr(dev), desc, _lib.ptr(u),
+              _lib.ptr(m0_), _lib.ptr(lp0_), _lib.ptr(f_), _lib.ptr(b_), _lib.ptr(lq_), _lib.ptr(ys), _lib.ptr(grad))
     return grad
 
 
 def independent_factory(M0, G0, Mt, Gt, gradient=False):
-    """``factory`` of independent.py:60-73: proposal N(u_t + (delta_t/2) grad_t, (delta_t/2) I)."""
+    """``factory`` of independent.py:60-73: proposal N(u_t + (delta_t/2) grad_t, (delta_t/2) I).
+
+    ``gradient=True`` reproduces the reference to the letter: ``GradientAuxiliaryG0`` (independent.py:173-190)
+    corrects the weight of every particle at t = 0, whereas ``GradientAuxiliaryGt`` (:252-268) sums its correction
+    over all particles -- a per-step constant that cancels in every normalisation.  ``gradient="per_particle"``
+    applies the per-particle correction at every step instead (the importance weight the proposal calls for)."""
     _check_family(M0, G0, Mt, Gt)
+    mode = {False: 0, True: 1, "per_particle": 2, 0: 0, 1: 1, 2: 2}[gradient]
 
     def factory(u, scale):
-        grad = grad_log_target(u, M0, G0, Mt, Gt) if gradient else None
-        return AuxiliaryFeynmanKac(M0, G0, Mt, Gt, _Aux(_lib.PROP_INDEPENDENT, u, scale, grad, gradient, None, None))
+        grad = grad_log_target(u, M0, G0, Mt, Gt) if mode else None
+        return AuxiliaryFeynmanKac(M0, G0, Mt, Gt, _Aux(_lib.PROP_INDEPENDENT, u, scale, grad, mode, None, None))
 
     return factory
 
 
 def get_independent_kernel(M0, G0, Mt, Gt, N, backward=False, Pt=None, gradient=False, parallel=False, *,
                            resampling="multinomial", return_history=False):
-    """Auxiliary particle Gibbs with independent (separable) proposals (independent.py:18-75)."""
+    """Auxiliary particle Gibbs with independent (separable) proposals (independent.py:18-75).
+    ``gradient``: ``False`` / ``True`` (the reference's weights, see ``independent_factory``) / ``"per_particle"``."""
     if parallel:
         raise NotImplementedError("parallel-in-time cSMC (independent.py:78-118, _primitives/csmc/pit) is out of "
                                   "scope of this build (SURVEY section 8(f), rank 3)")
@@ -325,6 +367,11 @@ def guided_factory(M0, G0, Mt, Gt):
     _check_family(M0, G0, Mt, Gt)
 
     def factory(u, scale):
+        # the gains are computed once from chain 0's schedule: every chain must share it.  `_aux_u` hands over a
+        # stride-0 (expanded) chain axis when delta is a scalar or [T]; a genuine [C, T] delta is rejected.
+        if scale.dim() == 2 and scale.shape[0] > 1 and scale.stride(0) != 0:
+            raise AuxssmError("guided_factory needs one delta schedule shared by all chains (scalar or [T]); "
+                              "got a per-chain [C, T] delta")
         K, cL = guided_gains(M0.P0.to(u), Mt.Q.to(u), scale[0].contiguous())
         return AuxiliaryFeynmanKac(M0, G0, Mt, Gt, _Aux(_lib.PROP_GUIDED, u, scale, None, False, K, cL))
 
@@ -365,6 +412,19 @@ def killing(uniforms_kill, uniforms, weights):
     _lib.call("auxssm_resample_killing_" + _lib.suffix(w.dtype), _lib.stream_ptr(dev), w.shape[0], w.shape[1],
               _lib.ptr(w), _lib.ptr(uk), _lib.ptr(u), _lib.ptr(idx))
     return idx.reshape(weights.shape)
+
+
+def systematic(uniforms3, weights, N=None):
+    """Conditional systematic resampling (resamplings.py:40-86): ``weights [..., M]``, the three uniforms (U, V, W)
+    of resamplings.py:65 as ``uniforms3 [..., 3]``; returns ``N`` (default ``M``) int32 indices per row."""
+    dev = _lib.require_cuda(weights, uniforms3)
+    w, u = _rows(weights), _rows(uniforms3)
+    M = w.shape[1]
+    N = M if N is None else int(N)
+    idx = torch.empty((w.shape[0], N), dtype=torch.int32, device=dev)
+    _lib.call("auxssm_resample_systematic_" + _lib.suffix(w.dtype), _lib.stream_ptr(dev), w.shape[0], M, N, _lib.ptr(w),
+              _lib.ptr(u), _lib.ptr(idx))
+    return idx.reshape(weights.shape[:-1] + (N,))
 
 
 def categorical(uniforms, weights):

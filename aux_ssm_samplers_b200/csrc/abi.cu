@@ -13,6 +13,17 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
+static thread_local char g_log[4096] = "";
+static thread_local size_t g_log_len = 0;
+
+void note_dispatch(const char* who) {
+  const size_t n = strlen(who);
+  if (g_log_len + n + 2 >= sizeof(g_log)) return;  // bounded: later launches are simply not recorded
+  if (g_log_len) g_log[g_log_len++] = ';';
+  memcpy(g_log + g_log_len, who, n + 1);
+  g_log_len += n;
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -77,3 +88,9 @@ int check_desc(const auxssm_lgssm_desc* d, const char* who) {
 extern "C" __attribute__((visibility("default"))) const char* auxssm_last_error(void) { return auxssm::g_err; }
 extern "C" __attribute__((visibility("default"))) int32_t auxssm_version(void) { return AUXSSM_VERSION; }
 extern "C" __attribute__((visibility("default"))) int64_t auxssm_launch_count(void) { return auxssm::launches(); }
+extern "C" __attribute__((visibility("default"))) const char* auxssm_dispatch_log(int32_t reset) {
+  static thread_local char out[4096];
+  memcpy(out, auxssm::g_log, sizeof(out));
+  if (reset) { auxssm::g_log[0] = 0; auxssm::g_log_len = 0; }
+  return out;
+}

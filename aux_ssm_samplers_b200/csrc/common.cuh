@@ -11,6 +11,7 @@ namespace auxssm {
 
 void set_error(const char* fmt, ...);
 void count_launch();
+void note_dispatch(const char* who);  // appends to the calling thread's dispatch log (auxssm_dispatch_log)
 
 inline int padded_dim(int d) {
   if (d <= 4) return 4;
@@ -42,7 +43,50 @@ __host__ __device__ inline int64_t unit_off(const auxssm_stride& s, int c, int b
       return AUXSSM_ERR_LAUNCH;                                               \
     }                                                                         \
     auxssm::count_launch();                                                   \
+    auxssm::note_dispatch(who);                                               \
   } while (0)
+
+// ---- AUXSSM_FLAG_F_IS_DIAGONAL is a HINT, verified on the device on every call -------------------------------
+// `count_offdiag_kernel` counts the non-zero off-diagonal entries of every F the call can read into gate[0]
+// (zeroed by a cudaMemsetAsync on the same stream).  The structured kernels (which read diag(F) only) start with
+// `if (*gate != 0) return;`, the general kernels launched right behind them with `if (*gate == 0) return;`:
+// exactly one of the two does the work, so a wrong hint costs time, never correctness, and nothing synchronises.
+template <typename T>
+__global__ void count_offdiag_kernel(const T* __restrict__ F, auxssm_stride st, int d, int n_chains, int n_batch,
+                                     int* gate) {
+  const int nc = st.chain != 0 ? n_chains : 1, nb = st.batch != 0 ? n_batch : 1;
+  const int64_t total = (int64_t)nc * nb * d * d;
+  int bad = 0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = e / (d * d);
+    const int k = (int)(e - u * d * d), r = k / d, c = k - r * d;
+    const T v = F[(u / nb) * st.chain + (u % nb) * st.batch + k];
+    if (r != c && v != T(0)) bad = 1;
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicAdd(gate, 1);
+}
+
+template <typename T>
+inline int launch_count_offdiag(cudaStream_t st, const T* F, const auxssm_lgssm_desc& d, int* gate) {
+  if (cudaMemsetAsync(gate, 0, sizeof(int), st) != cudaSuccess) {
+    set_error("auxssm: cudaMemsetAsync(gate) failed");
+    return AUXSSM_ERR_LAUNCH;
+  }
+  const int nc = d.Fs.chain != 0 ? d.n_chains : 1, nb = d.Fs.batch != 0 ? d.n_batch : 1;
+  const int64_t total = (int64_t)nc * nb * d.dx * d.dx;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 592) grid = 592;
+  count_offdiag_kernel<T><<<grid, 256, 0, st>>>(F, d.Fs, d.dx, d.n_chains, d.n_batch, gate);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("auxssm: count_offdiag launch failed: %s", cudaGetErrorString(e));
+    return AUXSSM_ERR_LAUNCH;
+  }
+  count_launch();
+  return AUXSSM_OK;
+}
+
+constexpr size_t kGateBytes = 256;  // scratch header holding the gate word
 
 template <typename K> inline int ensure_smem(K kernel, size_t bytes, const char* who) {
   if (bytes > device_max_smem()) {

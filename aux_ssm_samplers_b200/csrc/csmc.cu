@@ -61,7 +61,7 @@ static int check_csmc_desc(const auxssm_csmc_desc* d, const char* who) {
   if (d->N > 1024) { set_error("%s: N = %d exceeds 1024 particles", who, d->N); return AUXSSM_ERR_UNSUPPORTED; }
   if (d->d > 32) { set_error("%s: d = %d exceeds 32", who, d->d); return AUXSSM_ERR_UNSUPPORTED; }
   if (d->proposal < 0 || d->proposal > 2 || d->potential < 0 || d->potential > 2 || d->resampling < 0 ||
-      d->resampling > 1) {
+      d->resampling > 2) {
     set_error("%s: unknown proposal / potential / resampling id", who);
     return AUXSSM_ERR_INVALID;
   }
@@ -76,8 +76,10 @@ static int csmc_entry(void* stream, const auxssm_csmc_desc* d, const T* x_star, 
   const char* who = "auxssm_csmc_sweep";
   int rc = check_csmc_desc(d, who);
   if (rc) return rc;
-  if (!x_star || !m0 || !Lp0 || !F || !b || !Lq || !normals || !u_bwd || !x_out || !anc || (d->T > 1 && !u_res)) {
-    set_error("%s: null data pointer", who);
+  const bool rng_on = !normals && !u_res && !u_kill && !u_bwd;  // in-kernel Philox draws
+  if (!x_star || !m0 || !Lp0 || !F || !b || !Lq || !x_out || !anc ||
+      (!rng_on && (!normals || !u_bwd || (d->T > 1 && !u_res)))) {
+    set_error("%s: null data pointer (pass all draw arrays, or none of them for in-kernel draws)", who);
     return AUXSSM_ERR_INVALID;
   }
   if (d->potential != AUXSSM_POT_FLAT && !ys) { set_error("%s: potential needs ys", who); return AUXSSM_ERR_INVALID; }
@@ -89,7 +91,7 @@ static int csmc_entry(void* stream, const auxssm_csmc_desc* d, const T* x_star, 
     set_error("%s: guided proposal needs K and chol_Lam (auxssm_guided_gains)", who);
     return AUXSSM_ERR_INVALID;
   }
-  if (d->resampling == AUXSSM_RESAMPLE_KILLING && d->T > 1 && !u_kill) {
+  if (!rng_on && d->resampling == AUXSSM_RESAMPLE_KILLING && d->T > 1 && !u_kill) {
     set_error("%s: killing resampling needs u_kill", who);
     return AUXSSM_ERR_INVALID;
   }
@@ -103,6 +105,10 @@ static int csmc_entry(void* stream, const auxssm_csmc_desc* d, const T* x_star, 
   a.x_star = x_star; a.m0 = m0; a.Lp0 = Lp0; a.F = F; a.b = b; a.Lq = Lq; a.ys = ys; a.u = u; a.shd = shd;
   a.grad = grad; a.K = K; a.cL = cL; a.normals = normals; a.u_res = u_res; a.u_kill = u_kill; a.u_bwd = u_bwd;
   a.x_out = x_out; a.anc = anc;
+  a.rng.on = rng_on ? 1 : 0;
+  a.rng.seed = d->rng_seed;
+  a.rng.call0 = d->rng_counter;
+  a.rng_counter = rng_on ? d->rng_counter_ptr : nullptr;
   int max_slots = 0;
   if (full_hist) {
     a.xs_hist = xs_hist; a.lw_hist = lw_hist; a.a_hist = a_hist; a.hist_per_chain = 1;
@@ -243,6 +249,35 @@ __global__ void __launch_bounds__(1024) csmc_primitive_kernel(int N, const T* __
   }
 }
 
+// Conditional systematic resampling of M weights into N indices (resamplings.py:40-86); u3 = (U, V, W) per row.
+template <typename T>
+__global__ void __launch_bounds__(1024) csmc_systematic_kernel(int M, int N, const T* __restrict__ w_in,
+                                                               const T* __restrict__ u3, int32_t* __restrict__ idx) {
+  __shared__ T red[64];
+  __shared__ T cdf[1024];
+  const int64_t row = blockIdx.x;
+  const int i = threadIdx.x;
+  const T w = (i < M) ? w_in[row * M + i] : T(0);
+  const T cd = block_cdf<T>(w, red);
+  if (i < M) cdf[i] = cd;
+  __syncthreads();
+  if (i < N) {
+    const SysPlan<T> pl = systematic_plan<T>(cdf, N, u3[row * 3], u3[row * 3 + 1], u3[row * 3 + 2]);
+    idx[row * N + i] = search_left<T>(cdf, pl.r(i, N), M);
+  }
+}
+
+template <typename T>
+static int systematic_entry(void* stream, int64_t n_rows, int32_t M, int32_t N, const T* w, const T* u3, int32_t* idx) {
+  const char* who = "auxssm_resample_systematic";
+  if (n_rows < 1 || M < 1 || N < 1 || !w || !u3 || !idx) { set_error("%s: invalid argument", who); return AUXSSM_ERR_INVALID; }
+  if (M > 1024 || N > 1024) { set_error("%s: M = %d / N = %d exceed 1024", who, M, N); return AUXSSM_ERR_UNSUPPORTED; }
+  const int n = M > N ? M : N, ntb = (n + 31) / 32 * 32;
+  csmc_systematic_kernel<T><<<(unsigned)n_rows, ntb, 0, static_cast<cudaStream_t>(stream)>>>(M, N, w, u3, idx);
+  AUXSSM_CHECK_LAUNCH(who);
+  return AUXSSM_OK;
+}
+
 template <typename T, int OP>
 static int primitive_entry(void* stream, int64_t n_rows, int32_t N, const T* in, const T* u, const T* u_kill, T* wout,
                            int32_t* idx, const char* who) {
@@ -323,3 +358,12 @@ AUXSSM_API int32_t auxssm_guided_gains_f64(void* stream, int32_t T, int32_t d, c
   }
 AUXSSM_PRIMS(f32, float)
 AUXSSM_PRIMS(f64, double)
+
+extern "C" __attribute__((visibility("default"))) int32_t auxssm_resample_systematic_f32(
+    void* stream, int64_t n_rows, int32_t M, int32_t N, const float* w, const float* u3, int32_t* idx) {
+  return auxssm::systematic_entry<float>(stream, n_rows, M, N, w, u3, idx);
+}
+extern "C" __attribute__((visibility("default"))) int32_t auxssm_resample_systematic_f64(
+    void* stream, int64_t n_rows, int32_t M, int32_t N, const double* w, const double* u3, int32_t* idx) {
+  return auxssm::systematic_entry<double>(stream, n_rows, M, N, w, u3, idx);
+}

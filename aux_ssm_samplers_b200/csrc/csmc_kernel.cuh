@@ -15,6 +15,7 @@
 // (#resident CTAs) x history, independent of the number of chains.
 #pragma once
 #include "common.cuh"
+#include "philox.cuh"
 #include "smem_linalg.cuh"
 
 namespace auxssm {
@@ -28,6 +29,29 @@ template <typename T> struct CsmcArgs {
   T* lw_hist;
   int32_t* a_hist;
   int hist_per_chain;  // 1: history arrays are [n_chains, ...] outputs; 0: [gridDim.x, ...] scratch slots
+  RngCtl rng;          // in-kernel Philox draws when the draw pointers are NULL (philox.cuh)
+  const uint64_t* rng_counter;  // optional device-side call counter overriding rng.call0 (CUDA-graph replays)
+
+  // element `e` of the logical draw arrays (same layout as the external ones)
+  __device__ __forceinline__ uint64_t call0() const { return rng_counter ? rng_counter[0] : rng.call0; }
+  __device__ __forceinline__ uint64_t call_bwd() const { return call0() + (d.resampling == AUXSSM_RESAMPLE_KILLING ? 3 : 2); }
+  __device__ __forceinline__ T draw_u_res(int64_t e) const {
+    return rng.on ? philox_elem<T>(PHILOX_UNIFORM, rng.seed, call0() + 1, (uint64_t)e) : u_res[e];
+  }
+  __device__ __forceinline__ T draw_u_kill(int64_t e) const {
+    return rng.on ? philox_elem<T>(PHILOX_UNIFORM, rng.seed, call0() + 2, (uint64_t)e) : u_kill[e];
+  }
+  __device__ __forceinline__ T draw_u_bwd(int64_t e) const {
+    return rng.on ? philox_elem<T>(PHILOX_UNIFORM, rng.seed, call_bwd(), (uint64_t)e) : u_bwd[e];
+  }
+  template <int NMAX> __device__ __forceinline__ void draw_normals(int64_t e0, int n, T (&out)[NMAX]) const {
+    if (rng.on) {
+      philox_run<T, NMAX>(PHILOX_NORMAL, rng.seed, call0(), (uint64_t)e0, n, out);
+    } else {
+#pragma unroll
+      for (int k = 0; k < NMAX; ++k) if (k < n) out[k] = normals[e0 + k];
+    }
+  }
 };
 
 template <typename T> __device__ __forceinline__ T log_2pi_half() { return T(0.91893853320467274178); }
@@ -107,6 +131,45 @@ template <typename T> __device__ __forceinline__ int search_left(const T* cdf, T
     if (cdf[mid] < r) lo = mid + 1; else hi = mid;
   }
   return lo < n - 1 ? lo : n - 1;
+}
+
+// Conditional systematic resampling (resamplings.py:40-86; Chopin & Singh Alg. 4) from the three uniforms
+// (U, V, W) of resamplings.py:65.  Every thread evaluates the plan redundantly (a handful of flops, no barrier).
+// The grid r_j = (j + uniform) / N is increasing, so searchsorted gives a non-decreasing index vector whose zeros
+// are its first n_zero entries: zero_loc[k] = k, and the roll of :84 is by shift = floor(n_zero W).  Particle i
+// therefore takes the ancestor of grid point (i + shift) mod N; no index exchange between threads is needed.
+// n_zero = #{j : r_j <= cdf[0]} is found by walking down from an over-estimate with the exact predicate.
+template <typename T> struct SysPlan {
+  T uniform;
+  int shift;
+  __device__ __forceinline__ T r(int i, int N) const {
+    int j = i + shift;
+    if (j >= N) j -= N;
+    if (j < 0) j += N;
+    return (T(j) + uniform) / T(N);
+  }
+};
+template <typename T> __device__ __forceinline__ SysPlan<T> systematic_plan(const T* cdf, int N, T U, T V, T W) {
+  SysPlan<T> pl;
+  const T w0 = cdf[0];  // the canonical CDF starts with the weight of particle 0 itself
+  const T tmp = T(N) * w0, fl = floor(tmp);
+  if (tmp <= T(1)) {
+    pl.uniform = tmp * U;
+  } else {
+    const T rem = tmp - fl, p_cond = rem * (fl + T(1)) / tmp;
+    pl.uniform = (V < p_cond) ? rem * U : rem + (T(1) - rem) * U;
+  }
+  int j = (int)floor(tmp - pl.uniform) + 2;
+  if (j > N - 1) j = N - 1;
+  for (; j >= 0; --j)
+    if ((T(j) + pl.uniform) / T(N) <= w0) break;
+  const int n_zero = j + 1;
+  pl.shift = 0;
+  if (n_zero != 1) {
+    const int roll = (int)floor(T(n_zero) * W);
+    pl.shift = (roll < n_zero) ? roll : -1;  // out-of-range gather of zero_loc (fill value -1), resamplings.py:82
+  }
+  return pl;
 }
 
 // ---- per-particle dense algebra in registers (matrices in shared memory, row stride D) -------------
@@ -359,21 +422,20 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
     // Software pipeline: the draws and per-step parameters of step t+1 are requested at the top of step t,
     // so no DRAM round trip sits on the (strictly sequential) critical path of the time loop.
     constexpr bool DIRECT = (D <= 4);  // normals read straight into registers (coalesced for small d)
-    T ur_n = T(0), uk_n = T(0), eps_n[D], xs_n = T(0), y_n = T(0), u_n = T(0), g_n = T(0), s_n = T(1);
+    T ur_n = T(0), uk_n = T(0), uw_n = T(0), eps_n[D], xs_n = T(0), y_n = T(0), u_n = T(0), g_n = T(0), s_n = T(1);
 #pragma unroll
     for (int k = 0; k < D; ++k) eps_n[k] = T(0);
     auto prefetch = [&](int tt) {  // everything step tt needs
       const bool go = tt < Tn;
       if (go && active) {
-        if (tt > 0) {
-          ur_n = a.u_res[((int64_t)c * (Tn - 1) + (tt - 1)) * N + i];
-          if (dsc.resampling == AUXSSM_RESAMPLE_KILLING) uk_n = a.u_kill[((int64_t)c * (Tn - 1) + (tt - 1)) * N + i];
+        if (tt > 0 && dsc.resampling == AUXSSM_RESAMPLE_SYSTEMATIC) {
+          const int64_t us = ((int64_t)c * (Tn - 1) + (tt - 1)) * 3;  // (U, V, W), broadcast loads
+          ur_n = a.draw_u_res(us); uk_n = a.draw_u_res(us + 1); uw_n = a.draw_u_res(us + 2);
+        } else if (tt > 0) {
+          ur_n = a.draw_u_res(((int64_t)c * (Tn - 1) + (tt - 1)) * N + i);
+          if (dsc.resampling == AUXSSM_RESAMPLE_KILLING) uk_n = a.draw_u_kill(((int64_t)c * (Tn - 1) + (tt - 1)) * N + i);
         }
-        if (DIRECT) {
-          const T* eg = a.normals + (((int64_t)c * Tn + tt) * N + i) * d;
-#pragma unroll
-          for (int k = 0; k < D; ++k) if (k < d) eps_n[k] = eg[k];
-        }
+        if (DIRECT) a.template draw_normals<D>((((int64_t)c * Tn + tt) * N + i) * d, d, eps_n);
       }
       if (go && i < D) {
         xs_n = (i < d) ? xstar[(int64_t)tt * d + i] : T(0);
@@ -396,13 +458,14 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
 #pragma unroll
       for (int k = 0; k < D; ++k) xp[k] = T(0);
       // take this step's prefetched values, then request the next step's
-      const T ur = ur_n, uk = uk_n, xs_c = xs_n, y_c = y_n, u_c = u_n, g_c = g_n, s_c = s_n;
+      const T ur = ur_n, uk = uk_n, uw = uw_n, xs_c = xs_n, y_c = y_n, u_c = u_n, g_c = g_n, s_c = s_n;
       T eps[D];
 #pragma unroll
       for (int k = 0; k < D; ++k) eps[k] = eps_n[k];
       prefetch(t + 1);
       if (!first && active) {
-        const T r = cdf[N - 1] * (T(1) - ur);
+        const T r = (dsc.resampling == AUXSSM_RESAMPLE_SYSTEMATIC) ? systematic_plan<T>(cdf, N, ur, uk, uw).r(i, N)
+                                                                   : cdf[N - 1] * (T(1) - ur);
         anc = search_left<T>(cdf, r, N);
         // killing: survive iff u_kill * max_j w_j < w_i  (max weight of the previous step kept in misc[0])
         if (dsc.resampling == AUXSSM_RESAMPLE_KILLING && uk * misc[0] < w) anc = i;
@@ -426,9 +489,13 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
           load_padded<T, D>(a.K + (int64_t)t * dsc.gains_time_stride, m.K, d);
           load_padded<T, D>(a.cL + (int64_t)t * dsc.gains_time_stride, m.cL, d);
         }
-        // normals of this step, staged with coalesced loads
-        const T* eg = a.normals + ((int64_t)c * Tn + t) * N * d;
-        for (int e = i; e < N * d; e += blockDim.x) stage[e] = eg[e];
+        // normals of this step, staged with coalesced loads (or generated in place)
+        const int64_t e0 = ((int64_t)c * Tn + t) * N * d;
+        if (a.rng.on) {
+          for (int e = i; e < N * d; e += blockDim.x) stage[e] = philox_elem<T>(PHILOX_NORMAL, a.rng.seed, a.call0(), (uint64_t)(e0 + e));
+        } else {
+          for (int e = i; e < N * d; e += blockDim.x) stage[e] = a.normals[e0 + e];
+        }
       } else if (PROP == AUXSSM_PROP_GUIDED && (t <= 1 || dsc.gains_time_stride != 0)) {
         load_padded<T, D>(a.K + (int64_t)t * dsc.gains_time_stride, m.K, d);
         load_padded<T, D>(a.cL + (int64_t)t * dsc.gains_time_stride, m.cL, d);
@@ -468,10 +535,10 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
     // ------------------------------------ backward pass ----------------------------------------------
     T* xo = a.x_out + (int64_t)c * Tn * d;
     int32_t* ao = a.anc + (int64_t)c * Tn;
-    const T* ub = a.u_bwd + (int64_t)c * Tn;
+    const int64_t ub = (int64_t)c * Tn;
     // B_T ~ Cat(w_T): index = #{j : cdf[j] < r}, clamped (csmc.py:111 / :131)
     {
-      const T r = cdf[N - 1] * (T(1) - ub[0]);
+      const T r = cdf[N - 1] * (T(1) - a.draw_u_bwd(ub));
       int B = __syncthreads_count(active && cdf[i] < r);
       if (B > N - 1) B = N - 1;
       if (i == B) {
@@ -486,12 +553,12 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
       __syncthreads();
     }
     if (dsc.backward) {
-      T ub_n = (Tn > 1) ? ub[1] : T(0);
+      T ub_n = (Tn > 1) ? a.draw_u_bwd(ub + 1) : T(0);
       for (int t = Tn - 2, k2 = 1; t >= 0; --t, ++k2) {
         T xt[D], xpred[D], xsel[D];
         T lwh = T(0);
         const T ub_c = ub_n;
-        if (t > 0) ub_n = ub[k2 + 1];
+        if (t > 0) ub_n = a.draw_u_bwd(ub + k2 + 1);
         {
           // history of step t, staged with coalesced loads
           const T* xg = xs_h + (int64_t)t * N * d;

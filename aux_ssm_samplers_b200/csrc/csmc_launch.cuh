@@ -25,7 +25,8 @@ static int launch_csmc_one(cudaStream_t st, CsmcArgs<T>& a, int max_slots, int* 
   if (slots_used) *slots_used = (int)grid;
   if (st == (cudaStream_t)-1) return AUXSSM_OK;  // planning only
   kern<<<(unsigned)grid, ntb, smem, st>>>(a);
-  AUXSSM_CHECK_LAUNCH("auxssm_csmc_sweep");
+  AUXSSM_CHECK_LAUNCH(MAXT > 256 ? "auxssm_csmc_sweep (csmc_sweep_kernel, <= 1024 threads)"
+                                 : "auxssm_csmc_sweep (csmc_sweep_kernel, <= 256 threads)");
   return AUXSSM_OK;
 }
 

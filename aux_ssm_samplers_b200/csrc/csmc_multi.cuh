@@ -117,11 +117,26 @@ __global__ void __launch_bounds__(256) csmc_multi_kernel(CsmcArgs<T> a) {
     auto prefetch = [&](int tt) {
       const bool go = tt < Tn;
       if (go && act) {
-        if (tt > 0) {
+        if (tt > 0 && dsc.resampling == AUXSSM_RESAMPLE_SYSTEMATIC) {
+          const int64_t us = ((int64_t)c * (Tn - 1) + (tt - 1)) * 3;  // (U, V, W), broadcast loads
+          ur_n[0] = a.draw_u_res(us); ur_n[1] = a.draw_u_res(us + 1); ur_n[2] = a.draw_u_res(us + 2);
+        } else if (tt > 0 && a.rng.on) {
+          philox_run<T, PPT>(PHILOX_UNIFORM, a.rng.seed, a.call0() + 1, (uint64_t)(((int64_t)c * (Tn - 1) + (tt - 1)) * N + p0), PPT, ur_n);
+          if (dsc.resampling == AUXSSM_RESAMPLE_KILLING)
+            philox_run<T, PPT>(PHILOX_UNIFORM, a.rng.seed, a.call0() + 2, (uint64_t)(((int64_t)c * (Tn - 1) + (tt - 1)) * N + p0), PPT, uk_n);
+        } else if (tt > 0) {
           ldv<T, PPT>(ur_n, a.u_res + ((int64_t)c * (Tn - 1) + (tt - 1)) * N + p0);
           if (dsc.resampling == AUXSSM_RESAMPLE_KILLING)
             ldv<T, PPT>(uk_n, a.u_kill + ((int64_t)c * (Tn - 1) + (tt - 1)) * N + p0);
         }
+        if (a.rng.on) {
+          T run[PPT * D];
+          philox_run<T, PPT * D>(PHILOX_NORMAL, a.rng.seed, a.call0(), (uint64_t)((((int64_t)c * Tn + tt) * N + p0) * d), PPT * d, run);
+#pragma unroll
+          for (int q = 0; q < PPT; ++q)
+#pragma unroll
+            for (int k = 0; k < D; ++k) if (k < d) eps_n[q][k] = run[(D == 1) ? q : q * d + k];
+        } else {
         const T* eg = a.normals + (((int64_t)c * Tn + tt) * N + p0) * d;
         if (D == 1) {
           T e4[PPT];
@@ -133,6 +148,7 @@ __global__ void __launch_bounds__(256) csmc_multi_kernel(CsmcArgs<T> a) {
           for (int q = 0; q < PPT; ++q)
 #pragma unroll
             for (int k = 0; k < D; ++k) if (k < d) eps_n[q][k] = eg[q * d + k];
+        }
         }
       }
       if (go && i < D) {
@@ -172,8 +188,14 @@ __global__ void __launch_bounds__(256) csmc_multi_kernel(CsmcArgs<T> a) {
         const T tot = cdf[N - 1];
         T r[PPT];
         int lo[PPT];
+        if (dsc.resampling == AUXSSM_RESAMPLE_SYSTEMATIC) {
+          const SysPlan<T> pl = systematic_plan<T>(cdf, N, ur[0], ur[1], ur[2]);
 #pragma unroll
-        for (int q = 0; q < PPT; ++q) { r[q] = tot * (T(1) - ur[q]); lo[q] = 0; }
+          for (int q = 0; q < PPT; ++q) { r[q] = pl.r(p0 + q, N); lo[q] = 0; }
+        } else {
+#pragma unroll
+          for (int q = 0; q < PPT; ++q) { r[q] = tot * (T(1) - ur[q]); lo[q] = 0; }
+        }
         for (int step = hb; step > 0; step >>= 1) {
 #pragma unroll
           for (int q = 0; q < PPT; ++q) {
@@ -261,7 +283,7 @@ __global__ void __launch_bounds__(256) csmc_multi_kernel(CsmcArgs<T> a) {
     // ------------------------------------ backward pass ----------------------------------------------
     T* xo = a.x_out + (int64_t)c * Tn * d;
     int32_t* ao = a.anc + (int64_t)c * Tn;
-    const T* ub = a.u_bwd + (int64_t)c * Tn;
+    const int64_t ub = (int64_t)c * Tn;
     // B = min(#{j : cdf[j] < r}, N - 1) (csmc.py:111 / :131): per-thread counts, warp add, one shared atomic per
     // warp; the owner of particle B then publishes it as the selected state.  All threads call (three barriers).
     auto select = [&](T r, const T (&xc)[PPT][D], int t) {
@@ -296,11 +318,11 @@ __global__ void __launch_bounds__(256) csmc_multi_kernel(CsmcArgs<T> a) {
     {
       if (i == 0) isel[0] = 0;
       __syncthreads();
-      const T r = cdf[N - 1] * (T(1) - ub[0]);
+      const T r = cdf[N - 1] * (T(1) - a.draw_u_bwd(ub));
       B_last = select(r, xn, Tn - 1);
     }
     if (dsc.backward) {
-      T ub_n = (Tn > 1) ? ub[1] : T(0);
+      T ub_n = (Tn > 1) ? a.draw_u_bwd(ub + 1) : T(0);
       T xt_n[PPT][D], lwh_n[PPT];
 #pragma unroll
       for (int q = 0; q < PPT; ++q) {
@@ -335,7 +357,7 @@ __global__ void __launch_bounds__(256) csmc_multi_kernel(CsmcArgs<T> a) {
           for (int k = 0; k < D; ++k) xt[q][k] = xt_n[q][k];
         }
         const T ub_c = ub_n;
-        if (t > 0) ub_n = ub[k2 + 1];
+        if (t > 0) ub_n = a.draw_u_bwd(ub + k2 + 1);
         fetch(t - 1);
         T xsel[D];
 #pragma unroll

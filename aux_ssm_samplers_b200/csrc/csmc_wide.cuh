@@ -233,7 +233,29 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
     int32_t* a_h = a.a_hist + hs * (int64_t)(Tn > 1 ? Tn - 1 : 0) * N;
     const T* xstar = a.x_star + (int64_t)c * Tn * d;
     const T* ysc = a.ys ? a.ys + (int64_t)c * dsc.ys_chain_stride : nullptr;
-    const T* nrm = a.normals + (int64_t)c * Tn * N * d;
+    // normals of step tt -> bufE ([N][LD] rows): asynchronous copy of the external array, or generated in place
+    auto stage_normals = [&](int tt) {
+      const int64_t e0 = ((int64_t)c * Tn + tt) * N * d;
+      if (a.rng.on) {
+        constexpr int PER = PhiloxPer<T>::N;
+        const uint64_t b0 = (uint64_t)e0 / PER, b1 = (uint64_t)(e0 + (int64_t)N * d - 1) / PER;
+        const uint64_t call = a.call0();
+        for (uint64_t blk = b0 + threadIdx.x; blk <= b1; blk += blockDim.x) {
+          T v[PER];
+          philox_block(PHILOX_NORMAL, a.rng.seed, call, blk, v);
+#pragma unroll
+          for (int q = 0; q < PER; ++q) {
+            const int64_t e = (int64_t)(blk * PER + q) - e0;
+            if (e >= 0 && e < (int64_t)N * d) {
+              const int n = (int)__umulhi((unsigned)e, magic), k = (int)e - n * d;
+              bufE[n * LD + k] = v[q];
+            }
+          }
+        }
+      } else {
+        stage_rows_async<T, LD>(bufE, a.normals + e0, N * d, d, magic);
+      }
+    };
     auto stage_gains = [&](int tt) {
       if (PROP == AUXSSM_PROP_GUIDED && tt < Tn && (tt <= 1 || dsc.gains_time_stride != 0)) {
         stage_rows_async<T, LD>(mK, a.K + (int64_t)tt * dsc.gains_time_stride, d * d, d, magic);
@@ -242,12 +264,15 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
     };
     T w = T(0);
     // register prefetch of the per-step scalars (one step ahead, as in csmc_sweep_kernel)
-    T ur_n = T(0), uk_n = T(0), xs_n = T(0), y_n = T(0), u_n = T(0), g_n = T(0), s_n = T(1);
+    T ur_n = T(0), uk_n = T(0), uw_n = T(0), xs_n = T(0), y_n = T(0), u_n = T(0), g_n = T(0), s_n = T(1);
     auto prefetch = [&](int tt) {
       const bool go = tt < Tn;
-      if (go && active && tt > 0) {
-        ur_n = a.u_res[((int64_t)c * (Tn - 1) + (tt - 1)) * N + i];
-        if (dsc.resampling == AUXSSM_RESAMPLE_KILLING) uk_n = a.u_kill[((int64_t)c * (Tn - 1) + (tt - 1)) * N + i];
+      if (go && active && tt > 0 && dsc.resampling == AUXSSM_RESAMPLE_SYSTEMATIC) {
+        const int64_t us = ((int64_t)c * (Tn - 1) + (tt - 1)) * 3;  // (U, V, W), broadcast loads
+        ur_n = a.draw_u_res(us); uk_n = a.draw_u_res(us + 1); uw_n = a.draw_u_res(us + 2);
+      } else if (go && active && tt > 0) {
+        ur_n = a.draw_u_res(((int64_t)c * (Tn - 1) + (tt - 1)) * N + i);
+        if (dsc.resampling == AUXSSM_RESAMPLE_KILLING) uk_n = a.draw_u_kill(((int64_t)c * (Tn - 1) + (tt - 1)) * N + i);
       }
       if (go && i < D) {
         xs_n = (i < d) ? xstar[(int64_t)tt * d + i] : T(0);
@@ -260,7 +285,7 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
       if (go && PROP != AUXSSM_PROP_BOOTSTRAP) s_n = a.shd[(int64_t)c * Tn + tt];
     };
     prefetch(0);
-    stage_rows_async<T, LD>(bufE, nrm, N * d, d, magic);
+    stage_normals(0);
     stage_gains(0);
     T* part = bufA;   // particles of the previous step (gather source)
     T* other = bufB;
@@ -268,12 +293,13 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
     // ------------------------------ forward conditional particle filter ------------------------------
     for (int t = 0; t < Tn; ++t) {
       const bool first = (t == 0);
-      const T ur = ur_n, uk = uk_n, xs_c = xs_n, y_c = y_n, u_c = u_n, g_c = g_n, s_c = s_n;
+      const T ur = ur_n, uk = uk_n, uw = uw_n, xs_c = xs_n, y_c = y_n, u_c = u_n, g_c = g_n, s_c = s_n;
       prefetch(t + 1);
       // (1) conditional resampling, (2) parent gather, xpred
       int anc = 0;
       if (!first && active) {
-        const T r = cdf[N - 1] * (T(1) - ur);
+        const T r = (dsc.resampling == AUXSSM_RESAMPLE_SYSTEMATIC) ? systematic_plan<T>(cdf, N, ur, uk, uw).r(i, N)
+                                                                   : cdf[N - 1] * (T(1) - ur);
         anc = search_left<T>(cdf, r, N);
         if (dsc.resampling == AUXSSM_RESAMPLE_KILLING && uk * misc[0] < w) anc = i;
         if (i == 0) anc = 0;
@@ -425,7 +451,7 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
         }
       }
       __syncthreads();
-      if (t + 1 < Tn) stage_rows_async<T, LD>(bufE, nrm + (int64_t)(t + 1) * N * d, N * d, d, magic);
+      if (t + 1 < Tn) stage_normals(t + 1);
       if (new_gains) cst_l = misc[1];
 
       // (4) prior residuals  z = (xn - xpred) W^T, history
@@ -532,11 +558,11 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
     // ------------------------------------ backward pass ----------------------------------------------
     T* xo = a.x_out + (int64_t)c * Tn * d;
     int32_t* ao = a.anc + (int64_t)c * Tn;
-    const T* ub = a.u_bwd + (int64_t)c * Tn;
+    const int64_t ub = (int64_t)c * Tn;
     T* cur = other;  // staging buffers of the backward pass: the two particle buffers, `part` read first
     T* nxt = part;
     {
-      const T r = cdf[N - 1] * (T(1) - ub[0]);
+      const T r = cdf[N - 1] * (T(1) - a.draw_u_bwd(ub));
       int B = __syncthreads_count(active && cdf[i] < r);
       if (B > N - 1) B = N - 1;
       if (i < D) {
@@ -549,12 +575,12 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
     }
     if (dsc.backward) {
       if (Tn > 1) stage_rows_async<T, LD>(cur, xs_h + (int64_t)(Tn - 2) * N * d, N * d, d, magic);
-      T ub_n = (Tn > 1) ? ub[1] : T(0);
+      T ub_n = (Tn > 1) ? a.draw_u_bwd(ub + 1) : T(0);
       T lwh_n = (Tn > 1 && active) ? lw_h[(int64_t)(Tn - 2) * N + i] : T(0);
       for (int t = Tn - 2, k2 = 1; t >= 0; --t, ++k2) {
         const T ub_c = ub_n, lwh = lwh_n;
         if (t > 0) {
-          ub_n = ub[k2 + 1];
+          ub_n = a.draw_u_bwd(ub + k2 + 1);
           if (active) lwh_n = lw_h[(int64_t)(t - 1) * N + i];
         }
         cp_async_wait_all();

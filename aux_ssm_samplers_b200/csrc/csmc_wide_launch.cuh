@@ -23,7 +23,7 @@ static int launch_csmc_wide(cudaStream_t st, CsmcArgs<T>& a, int max_slots, int*
   if (slots_used) *slots_used = (int)grid;
   if (st == (cudaStream_t)-1) return AUXSSM_OK;  // planning only
   kern<<<(unsigned)grid, WideCfg<T, D>::NT, smem, st>>>(a);
-  AUXSSM_CHECK_LAUNCH("auxssm_csmc_sweep");
+  AUXSSM_CHECK_LAUNCH(NPAD > 128 ? "auxssm_csmc_sweep (csmc_wide_kernel, NPAD 256)" : "auxssm_csmc_sweep (csmc_wide_kernel, NPAD 128)");
   return AUXSSM_OK;
 }
 
@@ -50,7 +50,7 @@ static int launch_csmc_multi(cudaStream_t st, CsmcArgs<T>& a, int max_slots, int
   if (slots_used) *slots_used = (int)grid;
   if (st == (cudaStream_t)-1) return AUXSSM_OK;  // planning only
   kern<<<(unsigned)grid, ntb, smem, st>>>(a);
-  AUXSSM_CHECK_LAUNCH("auxssm_csmc_sweep");
+  AUXSSM_CHECK_LAUNCH("auxssm_csmc_sweep (csmc_multi_kernel)");
   return AUXSSM_OK;
 }
 

@@ -35,6 +35,7 @@ template <typename T> struct FilterArgs {
   T* ellpart;  // [units][n_chunks]
   T* prefix;   // [units][n_chunks][dx + dx*dx]   filtering marginal at the END of chunk j
   T* agg;      // [units][n_chunks][3 dx^2 + 2 dx] chunk aggregates (A, C, J, b, eta)
+  int* gate;   // number of non-zero off-diagonal entries of F (common.cuh); nullptr when no hint was given
   int n_chunks, chunk_len;
 };
 
@@ -233,6 +234,7 @@ template <typename T, int D> __device__ __forceinline__ void store_state(const F
                                                                          const StepBuf<T, D>& s) {
   const int dx = a.d.dx;
   cta_sync<D>();
+  if (a.Ps == nullptr) return;  // ell-only call
   T* gm = a.ms + unit_off(a.d.ms, c, b) + (int64_t)t * a.d.ms.time;
   if (threadIdx.x < dx) gm[threadIdx.x] = s.m[threadIdx.x];
   store_mat<T, D>(a.Ps + unit_off(a.d.Ps, c, b) + (int64_t)t * a.d.Ps.time, s.P, dx, dx);
@@ -460,6 +462,7 @@ __device__ __forceinline__ void chunk_range(int j, int chunk_len, int T, int& t0
 // pass A (chunk 0) and pass C (chunks >= 1): the recursion over one chunk.
 template <typename T, int D, bool HID>
 __global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) filter_recursion_kernel(FilterArgs<T> a, int chunk_first) {
+  if (a.gate != nullptr && *a.gate == 0) return;  // the hint held: the structured kernel does this launch's work
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Carve<T, D> cv{reinterpret_cast<T*>(smem_raw)};
   constexpr int NT = Tile<D>::NT;
@@ -515,6 +518,7 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
   const int lane = threadIdx.x & 31, ty = lane / GX, tx = lane % GX;
   const int j = chunk_first + blockIdx.y, unit = blockIdx.x * WPC + wq;
   if (unit >= a.d.n_chains * a.d.n_batch) return;  // whole warp; only __syncwarp is used below
+  if (a.gate != nullptr && *a.gate != 0) return;   // F is not diagonal after all: the general kernel runs instead
   const int c = unit / a.d.n_batch, b = unit % a.d.n_batch;
   const int d = a.d.dx, Tn = a.d.T;
   int t0, t1;
@@ -559,8 +563,9 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
   const T* yg = a.ys + unit_off(a.d.ys, c, b);
   const T* rg = a.Rs + unit_off(a.d.Rs, c, b);
   const T* cg = a.cs ? a.cs + unit_off(a.d.cs, c, b) : nullptr;
-  T* msg = a.ms + unit_off(a.d.ms, c, b);
-  T* Psg = a.Ps + unit_off(a.d.Ps, c, b);
+  const bool want_out = a.Ps != nullptr;
+  T* msg = want_out ? a.ms + unit_off(a.d.ms, c, b) : nullptr;
+  T* Psg = want_out ? a.Ps + unit_off(a.d.Ps, c, b) : nullptr;
   const bool pairs_ok = (d & 1) == 0 && (a.d.Ps.time & 1) == 0 &&
                         (reinterpret_cast<uintptr_t>(Psg) % (2 * sizeof(T))) == 0;
   // prefetch the first step's observation
@@ -784,12 +789,16 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
     if (!(inc == inc)) inc = T(0);
     if (obs_mask != 0u) ell += inc;
     // ---- outputs: tile -> shared -> coalesced rows ----
+    // ell-only call (ms == Ps == NULL: the reverse proposal of kalman/generic.py:67 needs the likelihood only):
+    // nothing is staged or stored, except the chunk-0 state a later chunk starts from.
+    if (!want_out && !(t + 1 == t1 && j == 0 && j + 1 < a.n_chunks)) continue;
 #pragma unroll
     for (int r = 0; r < TM; ++r) {
       stv<T, TN>(stage + (ty * TM + r) * LDS_ + tx * TN, p[r]);
       if (tx == 0) mvec[ty * TM + r] = mreg[r];
     }
     __syncwarp();
+    if (!want_out) continue;
     T* Pt = Psg + (int64_t)t * a.d.Ps.time;
     if (pairs_ok) {
       // a lane owns four consecutive columns of a row (16-byte shared load, two 2-element global stores)
@@ -1043,7 +1052,7 @@ static FilterPlan make_plan(const auxssm_lgssm_desc* d, size_t es) {
   p.chunk_len = (n_elem + p.n_chunks - 1) / p.n_chunks;
   p.n_chunks = (n_elem + p.chunk_len - 1) / p.chunk_len;  // drop empty trailing chunks
   const size_t units = (size_t)d->n_chains * d->n_batch;
-  size_t off = 0;
+  size_t off = kGateBytes;  // [0, kGateBytes): the diagonal-F gate word
   p.off_ell = off; off = align_up(off + units * p.n_chunks * es, 256);
   p.off_prefix = off;
   if (p.n_chunks > 1) off = align_up(off + units * p.n_chunks * ((size_t)d->dx + (size_t)d->dx * d->dx) * es, 256);
@@ -1071,16 +1080,32 @@ static int launch_filter(cudaStream_t st, const FilterArgs<T>& a) {
                          (a.d.T == 1 || (a.d.Fs.time == 0 && a.d.Qs.time == 0 && a.d.bs.time == 0));
   constexpr int TD = (D == 64) ? 64 : 64, TNW = 4;
   const size_t smem_tile = filter_tile_smem_elems<TD, TNW>() * sizeof(T);
-  if (warp_path) {
-    filter_warp_kernel<T, (D >= 8 && D <= 32) ? D : 8><<<dim3((units + 3) / 4, 1), 128, 0, st>>>(a, 0);
-    AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (warp recursion, chunk 0)");
-  } else if (tile_path) {
-    filter_tile_kernel<T, TD, TNW><<<dim3(units, 1), 128, smem_tile, st>>>(a, 0);
-    AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (tile recursion, chunk 0)");
+  FilterArgs<T> g = a;  // arguments of the general kernel behind a structured one (gated the other way round)
+  const bool structured = warp_path || tile_path;
+  FilterArgs<T> as = a;
+  if (structured && a.d.T > 1) {
+    rc = launch_count_offdiag<T>(st, a.Fs, a.d, a.gate);
+    if (rc) return rc;
   } else {
-    rec<<<dim3(units, 1), NT, smem_step, st>>>(a, 0);
-    AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (recursion, chunk 0)");
+    as.gate = nullptr;
+    g.gate = nullptr;
   }
+  auto launch_rec = [&](int chunk_first, int n_y) -> int {
+    if (warp_path) {
+      filter_warp_kernel<T, (D >= 8 && D <= 32) ? D : 8><<<dim3((units + 3) / 4, n_y), 128, 0, st>>>(as, chunk_first);
+      AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (warp recursion)");
+    } else if (tile_path) {
+      filter_tile_kernel<T, TD, TNW><<<dim3(units, n_y), 128, smem_tile, st>>>(as, chunk_first);
+      AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (tile recursion)");
+    }
+    if (!structured || g.gate != nullptr) {
+      rec<<<dim3(units, n_y), NT, smem_step, st>>>(g, chunk_first);
+      AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (recursion)");
+    }
+    return AUXSSM_OK;
+  };
+  rc = launch_rec(0, 1);
+  if (rc) return rc;
   if (a.n_chunks > 1) {
     const size_t smem_scan = scan_smem_elems<D>() * sizeof(T);
     if (a.n_chunks > 2) {
@@ -1093,16 +1118,8 @@ static int launch_filter(cudaStream_t st, const FilterArgs<T>& a) {
       filter_prefix_kernel<T, D><<<units, NT, smem_scan, st>>>(a);
       AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (prefix)");
     }
-    if (warp_path) {
-      filter_warp_kernel<T, (D >= 8 && D <= 32) ? D : 8><<<dim3((units + 3) / 4, a.n_chunks - 1), 128, 0, st>>>(a, 1);
-      AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (warp recursion, chunks >= 1)");
-    } else if (tile_path) {
-      filter_tile_kernel<T, TD, TNW><<<dim3(units, a.n_chunks - 1), 128, smem_tile, st>>>(a, 1);
-      AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (tile recursion, chunks >= 1)");
-    } else {
-      rec<<<dim3(units, a.n_chunks - 1), NT, smem_step, st>>>(a, 1);
-      AUXSSM_CHECK_LAUNCH("auxssm_kalman_filter (recursion, chunks >= 1)");
-    }
+    rc = launch_rec(1, a.n_chunks - 1);
+    if (rc) return rc;
   }
   return AUXSSM_OK;
 }
@@ -1115,9 +1132,12 @@ static int filter_entry(void* stream, const auxssm_lgssm_desc* d, const T* ys, c
   int rc = check_desc(d, who);
   if (rc) return rc;
   const bool hid = (d->flags & AUXSSM_FLAG_H_IDENTITY) != 0;
-  if (!ys || !m0 || !P0 || !Rs || !ms || !Ps || !ell || (!hid && !Hs) ||
-      (d->T > 1 && (!Fs || !Qs || !bs))) {
+  if (!ys || !m0 || !P0 || !Rs || !ell || (!hid && !Hs) || (d->T > 1 && (!Fs || !Qs || !bs))) {
     set_error("%s: null data pointer", who);
+    return AUXSSM_ERR_INVALID;
+  }
+  if ((ms == nullptr) != (Ps == nullptr)) {
+    set_error("%s: ms and Ps must both be given or both be NULL (ell-only call)", who);
     return AUXSSM_ERR_INVALID;
   }
   if (hid && Hs != nullptr) { set_error("%s: Hs must be NULL with AUXSSM_FLAG_H_IDENTITY", who); return AUXSSM_ERR_INVALID; }
@@ -1134,6 +1154,7 @@ static int filter_entry(void* stream, const auxssm_lgssm_desc* d, const T* ys, c
   a.ellpart = reinterpret_cast<T*>(sb + p.off_ell);
   a.prefix = reinterpret_cast<T*>(sb + p.off_prefix);
   a.agg = reinterpret_cast<T*>(sb + p.off_agg);
+  a.gate = reinterpret_cast<int*>(sb);
   a.n_chunks = p.n_chunks;
   a.chunk_len = p.chunk_len;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

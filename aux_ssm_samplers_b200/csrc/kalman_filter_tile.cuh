@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(128, 2) filter_tile_kernel(FilterArgs<T> a, in
   constexpr int GY = 4 * NW, GX = 8, TM = D / GY, TN = D / GX, LDS_ = D + 4, NB = 4, RS = D + 4;
   constexpr int NWORDS = (D + 31) / 32;   // 32-bit words of the observation mask
   static_assert(TM == NB && TN % 2 == 0 && CPC >= 1, "tile shape: one block of four rows per thread row-group");
+  if (a.gate != nullptr && *a.gate != 0) return;  // F is not diagonal after all: the general kernel runs instead
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cq = threadIdx.x / NTC, tid = threadIdx.x % NTC;  // chain slot in the CTA, thread in the chain
   T* base = reinterpret_cast<T*>(smem_raw) + (size_t)cq * (D * LDS_ + 4 * D + 32);
@@ -78,8 +79,9 @@ __global__ void __launch_bounds__(128, 2) filter_tile_kernel(FilterArgs<T> a, in
   const T* yg = a.ys + unit_off(a.d.ys, c, b);
   const T* rg = a.Rs + unit_off(a.d.Rs, c, b);
   const T* cg = a.cs ? a.cs + unit_off(a.d.cs, c, b) : nullptr;
-  T* msg = a.ms + unit_off(a.d.ms, c, b);
-  T* Psg = a.Ps + unit_off(a.d.Ps, c, b);
+  const bool want_out = a.Ps != nullptr;  // ell-only call otherwise (see filter_warp_kernel)
+  T* msg = want_out ? a.ms + unit_off(a.d.ms, c, b) : nullptr;
+  T* Psg = want_out ? a.Ps + unit_off(a.d.Ps, c, b) : nullptr;
   const bool pairs_ok = (d & 1) == 0 && (a.d.Ps.time & 1) == 0 &&
                         (reinterpret_cast<uintptr_t>(Psg) % (2 * sizeof(T))) == 0;
   // thread tid < d carries observation entry tid, prefetched one step ahead
@@ -240,10 +242,13 @@ __global__ void __launch_bounds__(128, 2) filter_tile_kernel(FilterArgs<T> a, in
       if (lane == 0) red[wq] = part;
     }
     // ---- outputs: tile -> shared -> coalesced rows ----
+    const bool stage_now = want_out || (t + 1 == t1 && j == 0 && j + 1 < a.n_chunks);
+    if (stage_now) {
 #pragma unroll
-    for (int r = 0; r < TM; ++r) {
-      stv<T, TN>(stage + (ty * TM + r) * LDS_ + tx * TN, p[r]);
-      if (tx == 0) mvec[ty * TM + r] = mreg[r];
+      for (int r = 0; r < TM; ++r) {
+        stv<T, TN>(stage + (ty * TM + r) * LDS_ + tx * TN, p[r]);
+        if (tx == 0) mvec[ty * TM + r] = mreg[r];
+      }
     }
     chain_sync<NTC>(bar_id);
     if (NW > 1) {
@@ -254,6 +259,7 @@ __global__ void __launch_bounds__(128, 2) filter_tile_kernel(FilterArgs<T> a, in
     T inc = part - T(0.5) * quad;
     if (!(inc == inc)) inc = T(0);
     if (any_obs) ell += inc;
+    if (!want_out) { chain_sync<NTC>(bar_id); continue; }
     T* Pt = Psg + (int64_t)t * a.d.Ps.time;
     if (pairs_ok) {
       constexpr int LPR = D / 4, RPP = NTC / LPR;

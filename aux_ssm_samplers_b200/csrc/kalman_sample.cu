@@ -33,6 +33,7 @@ template <typename T> struct SampleArgs {
   const T *ms, *Ps, *Fs, *Qs, *bs, *eps;
   T* xs;
   T* steps;  // [wave units][T][dx*dx + dx]   (G_t^T, e_t); entry T-1 holds e = x_{T-1} only
+  int* gate; // diagonal-F gate (common.cuh): the LEAN kernel runs when *gate == 0, the general one otherwise
   int unit0, n_units;
 };
 
@@ -175,6 +176,7 @@ template <typename T, int D, bool LEAN> struct ElemCfg {
 template <typename T, int D, bool LEAN>
 __global__ void __launch_bounds__(Tile<D>::NT * ElemCfg<T, D, LEAN>::W, ElemCfg<T, D, LEAN>::MINB)
 sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
+  if (a.gate != nullptr && ((*a.gate != 0) == LEAN)) return;  // the other instantiation does this launch's work
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = Tile<D>::NT, LD = Tile<D>::LD, W = ElemCfg<T, D, LEAN>::W;
   T* p = reinterpret_cast<T*>(smem_raw) + (size_t)threadIdx.y * samp_smem_elems<D>(LEAN);
@@ -379,6 +381,11 @@ __global__ void __launch_bounds__(64) sample_replay_kernel(SampleArgs<T> a) {
   }
 }
 
+template <typename T> __global__ void poison_if_gate_kernel(const int* gate, T* p, int64_t n) {
+  if (*gate == 0) return;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) p[e] = T(NAN);
+}
+
 struct SamplePlan {
   size_t per_unit;  // bytes of scratch per unit
   int wave;         // units per wave
@@ -393,7 +400,7 @@ static SamplePlan make_sample_plan(const auxssm_lgssm_desc* d, size_t es) {
   if (wave < 1) wave = 1;
   if (wave > units) wave = units;
   p.wave = (int)wave;
-  p.total = (p.per_unit * wave + 255) / 256 * 256;
+  p.total = kGateBytes + (p.per_unit * wave + 255) / 256 * 256;  // [0, kGateBytes): the diagonal-F gate word
   return p;
 }
 
@@ -401,19 +408,42 @@ template <typename T, int D> static int launch_sample(cudaStream_t st, SampleArg
   constexpr int NT = Tile<D>::NT;
   const bool lean = (a.d.flags & AUXSSM_FLAG_F_IS_DIAGONAL) != 0 && a.d.T > 1 && a.d.Fs.time == 0 &&
                     a.d.Qs.time == 0 && a.d.bs.time == 0;
-  const int W = lean ? ElemCfg<T, D, true>::W : ElemCfg<T, D, false>::W;
-  const size_t smem = samp_smem_elems<D>(lean) * sizeof(T) * W;
-  int rc = lean ? ensure_smem(sample_elements_kernel<T, D, true>, smem, "auxssm_kalman_sample")
-                : ensure_smem(sample_elements_kernel<T, D, false>, smem, "auxssm_kalman_sample");
+  int rc = AUXSSM_OK;
+  a.gate = lean ? a.gate : nullptr;
+  if (lean) {
+    rc = launch_count_offdiag<T>(st, a.Fs, a.d, a.gate);
+    if (rc) return rc;
+  }
+  constexpr int WL = ElemCfg<T, D, true>::W, WG = ElemCfg<T, D, false>::W;
+  const size_t smem_l = samp_smem_elems<D>(true) * sizeof(T) * WL, smem_g = samp_smem_elems<D>(false) * sizeof(T) * WG;
+  if (lean) rc = ensure_smem(sample_elements_kernel<T, D, true>, smem_l, "auxssm_kalman_sample");
   if (rc) return rc;
+  // The general kernel does not fit the shared memory of one CTA at d = 64 in fp64.  Without the hint that is an
+  // AUXSSM_ERR_UNSUPPORTED; with the hint the structured kernel runs under the gate and, should the hint turn out
+  // to be false, a poison kernel fills the scratch with NaN instead: the call then returns NaN trajectories
+  // (loudly wrong), never silently wrong ones.
+  const bool general_fits = smem_g <= device_max_smem();
+  if (general_fits || !lean) {
+    rc = ensure_smem(sample_elements_kernel<T, D, false>, smem_g, "auxssm_kalman_sample");
+    if (rc) return rc;
+  }
   const int n_tiles = (a.d.T + kTileLen - 1) / kTileLen;
   for (int u0 = 0; u0 < units; u0 += wave) {
     a.unit0 = u0;
     a.n_units = (units - u0 < wave) ? units - u0 : wave;
-    const unsigned grid = (unsigned)(((int64_t)a.n_units * n_tiles + W - 1) / W);
-    if (lean) sample_elements_kernel<T, D, true><<<grid, dim3(NT, W), smem, st>>>(a, n_tiles);
-    else sample_elements_kernel<T, D, false><<<grid, dim3(NT, W), smem, st>>>(a, n_tiles);
-    AUXSSM_CHECK_LAUNCH("auxssm_kalman_sample (elements)");
+    const int64_t items = (int64_t)a.n_units * n_tiles;
+    if (lean) {
+      sample_elements_kernel<T, D, true><<<(unsigned)((items + WL - 1) / WL), dim3(NT, WL), smem_l, st>>>(a, n_tiles);
+      AUXSSM_CHECK_LAUNCH("auxssm_kalman_sample (elements, diagonal F)");
+    }
+    if (general_fits) {
+      sample_elements_kernel<T, D, false><<<(unsigned)((items + WG - 1) / WG), dim3(NT, WG), smem_g, st>>>(a, n_tiles);
+      AUXSSM_CHECK_LAUNCH("auxssm_kalman_sample (elements)");
+    } else {
+      const int64_t n = (int64_t)a.n_units * a.d.T * ((int64_t)a.d.dx * a.d.dx + a.d.dx);
+      poison_if_gate_kernel<T><<<592, 256, 0, st>>>(a.gate, a.steps, n);
+      AUXSSM_CHECK_LAUNCH("auxssm_kalman_sample (poison on a false diagonal-F hint)");
+    }
     sample_replay_kernel<T, D><<<a.n_units, 64, 0, st>>>(a);
     AUXSSM_CHECK_LAUNCH("auxssm_kalman_sample (replay)");
   }
@@ -431,16 +461,17 @@ static int sample_entry(void* stream, const auxssm_lgssm_desc* d, const T* ms, c
     return AUXSSM_ERR_INVALID;
   }
   SamplePlan p = make_sample_plan(d, sizeof(T));
-  if (scratch == nullptr || scratch_bytes < p.per_unit) {
-    set_error("%s: scratch too small (%zu bytes; one unit needs %zu)", who, scratch_bytes, p.per_unit);
+  if (scratch == nullptr || scratch_bytes < kGateBytes + p.per_unit) {
+    set_error("%s: scratch too small (%zu bytes; one unit needs %zu)", who, scratch_bytes, kGateBytes + p.per_unit);
     return AUXSSM_ERR_SCRATCH;
   }
   int wave = p.wave;
-  if (scratch_bytes < p.total) wave = (int)(scratch_bytes / p.per_unit);  // smaller scratch => more waves
+  if (scratch_bytes < p.total) wave = (int)((scratch_bytes - kGateBytes) / p.per_unit);  // smaller scratch => more waves
   SampleArgs<T> a;
   a.d = *d;
   a.ms = ms; a.Ps = Ps; a.Fs = Fs; a.Qs = Qs; a.bs = bs; a.eps = eps; a.xs = xs;
-  a.steps = static_cast<T*>(scratch);
+  a.gate = static_cast<int*>(scratch);
+  a.steps = reinterpret_cast<T*>(static_cast<unsigned char*>(scratch) + kGateBytes);
   a.unit0 = 0; a.n_units = 0;
   const int units = d->n_chains * d->n_batch;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -220,6 +220,15 @@ __global__ void __launch_bounds__(NTB) logpdf_fast_kernel(LogpdfFastArgs<T> fa) 
     sc[i] = (do_lik && a.cs != nullptr && i < dx) ? a.cs[unit_off(a.d.cs, c, b) + i] : T(0);
   }
   __syncthreads();
+  // AUXSSM_FLAG_F_IS_DIAGONAL is a hint: the whole F is in shared memory anyway, so it is verified here and the
+  // diagonal shortcut is only taken when it holds (a wrong hint costs time, never correctness).
+  bool f_diag = (a.d.flags & AUXSSM_FLAG_F_IS_DIAGONAL) != 0;
+  if (f_diag) {
+    int off = 0;
+    for (int e = threadIdx.x; e < D * D; e += NTB)
+      if ((e / D) != (e % D) && sF[e] != T(0)) off = 1;
+    f_diag = __syncthreads_or(off) == 0;
+  }
   const T cst = (do_prior && Tn > 1) ? prep[dx * dx + dx] : T(0);
   const int t = blockIdx.y * NTB + threadIdx.x;
   T total = T(0);
@@ -234,7 +243,7 @@ __global__ void __launch_bounds__(NTB) logpdf_fast_kernel(LogpdfFastArgs<T> fa) 
 #pragma unroll
       for (int i = 0; i < D; ++i) z[i] = (i < dx) ? xp[i] : T(0);  // z <- x_{t-1}
       T r[D];
-      if (a.d.flags & AUXSSM_FLAG_F_IS_DIAGONAL) {  // promise of the caller: F x is one multiply per entry
+      if (f_diag) {  // verified above: F x is one multiply per entry
 #pragma unroll
         for (int i = 0; i < D; ++i) r[i] = x[i] - fma_(sF[i * D + i], z[i], sb[i]);
       } else {

@@ -81,29 +81,46 @@ def _next_fast_len(n):
     return best
 
 
-def effective_sample_size(samples, var=None):
-    """ESS of ``samples`` [C_local, n] over all ranks' chains, after ``ess.py:28-161``."""
+def chain_autocovariances(samples):
+    """Per-chain means ``[C]`` and biased autocovariances ``[C, n]`` (float64) of ``samples [C, n]``.
+    CUDA tensors go through ``auxssm_autocov_*`` (direct sums in double); CPU tensors (the gloo tests) through an
+    FFT, as ``ess.py:69-79`` does."""
+    c_local, n = samples.shape
+    if samples.is_cuda and samples.dtype in (torch.float32, torch.float64):
+        from . import _lib
+        x = samples.contiguous()
+        mean = torch.empty((c_local,), dtype=torch.float64, device=x.device)
+        acov = torch.empty((c_local, n), dtype=torch.float64, device=x.device)
+        _lib.call("auxssm_autocov_" + _lib.suffix(x.dtype), _lib.stream_ptr(x.device), c_local, n, _lib.ptr(x),
+                  _lib.ptr(mean), _lib.ptr(acov))
+        return mean, acov
     x = samples.double()
-    c_local, n = x.shape
-    mean_chain = x.mean(1, keepdim=True)
-    centered = x - mean_chain
+    mean = x.mean(1)
+    centered = x - mean[:, None]
     m = _next_fast_len(2 * n)
     f = torch.fft.rfft(centered, n=m, dim=1)
-    acov = torch.fft.irfft(f * torch.conj(f), n=m, dim=1)[:, :n] / n       # [C_local, n]
+    return mean, torch.fft.irfft(f * torch.conj(f), n=m, dim=1)[:, :n] / n
+
+
+def effective_sample_size(samples, var=None):
+    """ESS of ``samples`` [C_local, n] over all ranks' chains, after ``ess.py:28-161``."""
+    c_local, n = samples.shape
+    dev = samples.device
+    mean_chain, acov = chain_autocovariances(samples)
     acov_sum = _all_reduce_sum(acov.sum(0))                                 # sum over ALL chains
-    n_chains = int(_all_reduce_sum(torch.tensor([float(c_local)], dtype=torch.float64, device=x.device)).item())
-    mean_acov = acov_sum / n_chains                                         # ess.py:80
-    means = all_gather_chains(mean_chain[:, 0])
+    n_chains = int(_all_reduce_sum(torch.tensor([float(c_local)], dtype=torch.float64, device=dev)).item())
+    means = all_gather_chains(mean_chain).cpu().tolist()
+    mean_acov = (acov_sum / n_chains).cpu().tolist()                        # ess.py:80
+    # everything below is O(n) scalar work on the host (ess.py:81-161)
     mean_var0 = mean_acov[0] * n / (n - 1.0)
     weighted_var = mean_var0 * (n - 1.0) / n
-    if n_chains > 1:
-        weighted_var = weighted_var + means.var(unbiased=True)              # ess.py:87-93
+    if n_chains > 1:                                                        # ess.py:87-93
+        mbar = sum(means) / n_chains
+        weighted_var = weighted_var + sum((v - mbar) ** 2 for v in means) / (n_chains - 1.0)
     if var is not None:
-        weighted_var = torch.as_tensor(float(var), dtype=torch.float64, device=x.device)
-        mean_var0 = weighted_var.clone()
+        weighted_var = mean_var0 = float(var)
     n_even = n - n % 2
-    rho = torch.cat([torch.ones(1, dtype=torch.float64, device=x.device),
-                     1.0 - (mean_var0 - mean_acov[1:n_even]) / weighted_var]).cpu().tolist()
+    rho = [1.0] + [1.0 - (mean_var0 - mean_acov[t]) / weighted_var for t in range(1, n_even)]
     rho_even, rho_odd = rho[0::2], rho[1::2]
     k_pairs = len(rho_odd)
     rho_even = rho_even[:k_pairs] if len(rho_even) > k_pairs else rho_even
@@ -114,10 +131,13 @@ def effective_sample_size(samples, var=None):
         mask.append(carry)
         if carry:
             max_t = t
-    idx = min(max_t + 1, k_pairs - 1)
     odd = [rho_odd[t] if mask[t] else 0.0 for t in range(k_pairs)]
     mask_even = list(mask)
-    mask_even[idx] = rho_even[idx] > 0
+    # ess.py:131 `mask.at[max_t + 1].set(...)`: an out-of-bounds scatter is DROPPED by XLA, whereas the gathers
+    # `rho_hat_even[indices]` (:131, :156) clamp the index
+    if max_t + 1 < k_pairs:
+        mask_even[max_t + 1] = rho_even[max_t + 1] > 0
+    idx = min(max_t + 1, k_pairs - 1)
     even = [rho_even[t] if mask_even[t] else 0.0 for t in range(k_pairs)]
     # Geyer's initial monotone sequence (ess.py:137-149)
     prev = even[0] + odd[0]

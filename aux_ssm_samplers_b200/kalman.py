@@ -183,14 +183,16 @@ def _prep_lgssm(d, dims, lgssm, dtype):
 # primitives
 # --------------------------------------------------------------------------------------------
 
-def filtering(ys, lgssm, parallel, *, inner_batch=False, time_chunks=0, f_diagonal=False):
+def filtering(ys, lgssm, parallel, *, inner_batch=False, time_chunks=0, f_diagonal=False, marginals=True):
     """Kalman filter; returns ``(ms, Ps, ell)`` like the reference (filtering.py:18-46).
+    ``marginals=False`` is the ell-only call (returns ``(None, None, ell)``; nothing but the likelihood is stored).
 
     ``ell`` is summed over the inner batch (filtering.py:43-45) and has shape ``[C]`` (or ``[]``).
     ``time_chunks`` (parallel only) forces the number of time chunks of the scan; 0 = automatic.
-    ``f_diagonal=True`` is a promise that every ``F_t`` is a diagonal matrix (layout unchanged); together
+    ``f_diagonal=True`` is a HINT that every ``F_t`` is a diagonal matrix (layout unchanged); together
     with ``Hs=None``, ``Rs=Diagonal(...)`` and time-invariant ``Fs, Qs, bs`` it selects the one-warp-per-chain
-    structured kernel.
+    structured kernel.  The library verifies the hint on the device on every call and runs the general kernels
+    when it does not hold: a wrong hint costs time, never correctness.
     """
     lgssm = LGSSM(*lgssm)
     dev = _lib.require_cuda(ys, *_tensors(lgssm))
@@ -201,10 +203,12 @@ def filtering(ys, lgssm, parallel, *, inner_batch=False, time_chunks=0, f_diagon
     d = _fill_desc(dims, parallel, time_chunks, hid, isinstance(lgssm.Rs, Diagonal), f_diagonal)
     p = _prep_lgssm(d, dims, lgssm, dtype)
     ysc, d.ys = _canon(ys, (dims.dy,), dims.T, dims, "ys")
-    ms = torch.empty(_out_shape(dims, dims.T, (dims.dx,)), dtype=dtype, device=dev)
-    Ps = torch.empty(_out_shape(dims, dims.T, (dims.dx, dims.dx)), dtype=dtype, device=dev)
-    _, d.ms = _canon(ms, (dims.dx,), dims.T, dims, "ms")
-    _, d.Ps = _canon(Ps, (dims.dx, dims.dx), dims.T, dims, "Ps")
+    ms = Ps = None
+    if marginals:
+        ms = torch.empty(_out_shape(dims, dims.T, (dims.dx,)), dtype=dtype, device=dev)
+        Ps = torch.empty(_out_shape(dims, dims.T, (dims.dx, dims.dx)), dtype=dtype, device=dev)
+        _, d.ms = _canon(ms, (dims.dx,), dims.T, dims, "ms")
+        _, d.Ps = _canon(Ps, (dims.dx, dims.dx), dims.T, dims, "Ps")
     ell = torch.empty((dims.C,), dtype=dtype, device=dev)
     L = _lib.lib()
     nbytes = L.auxssm_kalman_filter_scratch_bytes(d, ys.element_size())
@@ -224,6 +228,7 @@ def sampling(key, ms, Ps, lgssm, parallel, *, inner_batch=False, time_chunks=0, 
     dtype = ms.dtype
     sfx = _lib.suffix(dtype)
     eps = key if torch.is_tensor(key) else key.normal(tuple(ms.shape), dtype, dev)
+    _lib.require_cuda(ms, eps)
     if tuple(eps.shape) != tuple(ms.shape):
         raise AuxssmError("eps must have the shape of ms, got %s vs %s" % (tuple(eps.shape), tuple(ms.shape)))
     dims = _infer_dims(None, lgssm.m0, inner_batch, xs=ms)
@@ -250,7 +255,7 @@ def sampling(key, ms, Ps, lgssm, parallel, *, inner_batch=False, time_chunks=0, 
 
 def _logpdf(which, ys, xs, ell, lgssm, inner_batch, f_diagonal=False):
     lgssm = LGSSM(*lgssm)
-    dev = _lib.require_cuda(xs)
+    dev = _lib.require_cuda(xs, ys, ell if torch.is_tensor(ell) else None, *_tensors(lgssm))
     dtype = xs.dtype
     sfx = _lib.suffix(dtype)
     dims = _infer_dims(ys, lgssm.m0, inner_batch, xs=xs)
@@ -264,7 +269,7 @@ def _logpdf(which, ys, xs, ell, lgssm, inner_batch, f_diagonal=False):
     xsc, d.xs = _canon(xs, (dims.dx,), dims.T, dims, "xs")
     ellc = None
     if which & _lib.LOGPDF_MINUS_ELL:
-        ellc = ell.reshape(-1).to(dtype).contiguous()
+        ellc = torch.as_tensor(ell, dtype=dtype, device=dev).reshape(-1).contiguous()
         if ellc.numel() != dims.C:
             raise AuxssmError("ell must have one entry per chain")
     out = torch.empty((dims.C,), dtype=dtype, device=dev)
@@ -295,7 +300,7 @@ def log_likelihood(ys, xs, lgssm, *, inner_batch=False):
 
 def auxiliary_draw(x, normals, delta):
     """u = x + sqrt(delta / 2) * normals (generic.py:61); x is ``[C, ...]``, delta scalar or ``[C]``."""
-    dev = _lib.require_cuda(x, normals)
+    dev = _lib.require_cuda(x, normals, delta if torch.is_tensor(delta) and delta.dim() > 0 else None)
     sfx = _lib.suffix(x.dtype)
     x = x.contiguous()
     normals = normals.contiguous()
@@ -317,7 +322,7 @@ def _as_delta(delta, C, dtype, dev):
 
 def mh_accept(x, x_prop, u, delta, log_lgssm_prop, log_lgssm_rev, log_target_prop, log_target_rev, uniforms):
     """MH accept/reject of generic.py:70-74 / 98-106.  Returns (x_new, accepted[bool], alpha)."""
-    dev = _lib.require_cuda(x, x_prop, u)
+    dev = _lib.require_cuda(x, x_prop, u, log_lgssm_prop, log_lgssm_rev, log_target_prop, log_target_rev, uniforms)
     sfx = _lib.suffix(x.dtype)
     C = x.shape[0]
     dl = _as_delta(delta, C, x.dtype, dev)
@@ -353,7 +358,9 @@ def get_kernel(dynamics_factory, observations_factory, log_likelihood_fn, parall
         m0, P0, Fs, Qs, bs, *_ = dynamics_factory(x)
         ys, Hs, Rs, cs, *_ = observations_factory(x, u, delta)
         lgssm = LGSSM(m0, P0, Fs, Qs, bs, Hs, Rs, cs)
-        ms, Ps, ell = filtering(ys, lgssm, parallel, time_chunks=time_chunks, f_diagonal=f_diagonal)
+        # the reverse proposal (generic.py:67) only needs the likelihood: ell-only filter call, nothing stored
+        ms, Ps, ell = filtering(ys, lgssm, parallel, time_chunks=time_chunks, f_diagonal=f_diagonal,
+                                marginals=x_prop is None)
         if x_prop is None:
             x_prop = sampling(sampling_key, ms, Ps, lgssm, parallel, time_chunks=time_chunks,
                               f_diagonal=f_diagonal)

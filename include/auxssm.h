@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AUXSSM_VERSION 100
+#define AUXSSM_VERSION 200
 
 enum {
   AUXSSM_OK = 0,
@@ -54,7 +54,10 @@ typedef struct auxssm_stride {
 /* flags */
 #define AUXSSM_FLAG_H_IDENTITY 1u /* Hs == NULL: H_t = I (requires dy == dx), c_t = 0 if cs == NULL */
 #define AUXSSM_FLAG_R_DIAGONAL 2u /* Rs holds diag(R_t): core shape [dy] instead of [dy, dy]          */
-#define AUXSSM_FLAG_F_IS_DIAGONAL 4u /* hint: every F_t is a diagonal matrix (layout unchanged, [dx, dx]) */
+/* HINT: every F_t is probably diagonal (layout unchanged, [dx, dx]).  The library verifies it ON THE DEVICE on
+ * every call (no host synchronisation) and takes the structured kernels only when it holds; with a dense F the
+ * general kernels run and the results are the same as without the flag. */
+#define AUXSSM_FLAG_F_IS_DIAGONAL 4u
 
 /*
  * Linear-Gaussian state-space model, mirrors the LGSSM NamedTuple
@@ -79,10 +82,16 @@ const char* auxssm_last_error(void);
 int32_t auxssm_version(void);
 /* cumulative number of CUDA kernels this library has launched in the calling process */
 int64_t auxssm_launch_count(void);
+/* ';'-separated names of the kernels launched by the calling host thread since the last reset (diagnostics and
+ * tests: which code path served a call).  A structured kernel and the general kernel launched behind it under the
+ * diagonal-F gate both appear; exactly one of them does the work. */
+const char* auxssm_dispatch_log(int32_t reset);
 
 /* ---- Kalman filter: replaces filtering(ys, lgssm, parallel), filtering.py:18-46 ------------
  * Outputs ms, Ps (strides desc->ms, desc->Ps) and ell[n_chains] (summed over the inner batch,
- * filtering.py:43-45).  Missing observations are non-finite entries of ys (filtering.py:86-130). */
+ * filtering.py:43-45).  Missing observations are non-finite entries of ys (filtering.py:86-130).
+ * ms == Ps == NULL is an ELL-ONLY call: the marginals are not stored (the reverse proposal of
+ * kalman/generic.py:67 uses the likelihood only).  The scratch buffer is always required (>= 256 bytes). */
 size_t auxssm_kalman_filter_scratch_bytes(const auxssm_lgssm_desc* desc, int32_t elem_size);
 int32_t auxssm_kalman_filter_f32(void* stream, const auxssm_lgssm_desc* desc, const float* ys,
                                  const float* m0, const float* P0, const float* Fs, const float* Qs,
@@ -188,7 +197,8 @@ int32_t auxssm_sv_log_potential_f64(void* stream, int64_t n_chains, int64_t n_pe
  * Anything else must use the unfused primitives below, one call per time step.
  *
  * Draws are inputs (parity mode): normals[n_chains,T,N,d] (csmc.py:74,91), u_resample[n_chains,T-1,N]
- * (resamplings.py:35), u_kill[n_chains,T-1,N] (killing only), u_backward[n_chains,T] (csmc.py:111 /
+ * (resamplings.py:35; SYSTEMATIC: [n_chains,T-1,3] = the (U, V, W) of resamplings.py:65),
+ * u_kill[n_chains,T-1,N] (killing only), u_backward[n_chains,T] (csmc.py:111 /
  * :131,138).  Categorical draws follow jax.random.choice: idx = first j with cdf[j] >= cdf[N-1](1-U),
  * with the CDF accumulated in the library's canonical order.
  * Outputs: x_out[n_chains,T,d], ancestors[n_chains,T] (updated = ancestors != 0, csmc.py:59).
@@ -196,7 +206,7 @@ int32_t auxssm_sv_log_potential_f64(void* stream, int64_t n_chains, int64_t n_pe
  * anc_hist[n_chains,T-1,N].  N <= 1024, d <= 32.                                                      */
 enum { AUXSSM_PROP_BOOTSTRAP = 0, AUXSSM_PROP_INDEPENDENT = 1, AUXSSM_PROP_GUIDED = 2 };
 enum { AUXSSM_POT_FLAT = 0, AUXSSM_POT_GAUSSIAN = 1, AUXSSM_POT_SV = 2 };
-enum { AUXSSM_RESAMPLE_MULTINOMIAL = 0, AUXSSM_RESAMPLE_KILLING = 1 };
+enum { AUXSSM_RESAMPLE_MULTINOMIAL = 0, AUXSSM_RESAMPLE_KILLING = 1, AUXSSM_RESAMPLE_SYSTEMATIC = 2 };
 
 typedef struct auxssm_csmc_desc {
   int32_t T, N, d, n_chains;
@@ -206,6 +216,15 @@ typedef struct auxssm_csmc_desc {
   int64_t ys_chain_stride;  /* 0: one data set ys[T,d] shared by all chains; T*d: one per chain          */
   int64_t gains_time_stride;/* GUIDED: d*d if K / cholLam are [T,d,d], 0 if time-invariant [d,d]         */
   double sig;               /* GAUSSIAN potential: observation std                                       */
+  /* In-kernel draws.  When normals, u_resample, u_kill and u_backward are ALL NULL the sweep generates them itself
+   * with counter-based Philox4x32-10 (csrc/philox.cuh): the logical arrays documented above are reproduced element
+   * for element as auxssm_philox_{normal,uniform}_* would fill them with (rng_seed, call), call = rng_counter + 0
+   * (normals), + 1 (u_resample), + 2 (u_kill, killing only), then u_backward.  rng_counter_ptr (device memory, may
+   * be NULL) overrides rng_counter with the value stored there when the kernel runs (CUDA-graph replays; advance it
+   * with auxssm_philox_advance).  No draw ever touches HBM: 2N(d+1)s fewer bytes per (time step x chain).        */
+  uint64_t rng_seed;
+  uint64_t rng_counter;
+  const uint64_t* rng_counter_ptr;
 } auxssm_csmc_desc;
 
 size_t auxssm_csmc_scratch_bytes(const auxssm_csmc_desc* desc, int32_t elem_size);
@@ -238,6 +257,8 @@ int32_t auxssm_guided_gains_f64(void* stream, int32_t T, int32_t d, const double
  * multinomial    idx[r, :] conditional multinomial, idx[r, 0] = 0              resamplings.py:14-37
  * killing        idx = i if u_kill * max w < w_i else multinomial draw; idx[r, 0] = 0  (not in the reference)
  * categorical    one draw per row: jax.random.choice(key, N, p=w, shape=())    csmc.py:111,131,138
+ * systematic     conditional systematic resampling (Chopin & Singh Alg. 4) of M weights into N indices from the
+ *                three uniforms u3[r] = (U, V, W) of resamplings.py:65; idx[r, 0] = 0       resamplings.py:40-86
  * Arrays are [n_rows, N] contiguous, N <= 1024.                                                       */
 int32_t auxssm_normalize_f32(void* stream, int64_t n_rows, int32_t N, const float* log_w, float* w);
 int32_t auxssm_normalize_f64(void* stream, int64_t n_rows, int32_t N, const double* log_w, double* w);
@@ -249,10 +270,58 @@ int32_t auxssm_resample_killing_f32(void* stream, int64_t n_rows, int32_t N, con
                                     const float* u_kill, const float* u, int32_t* idx);
 int32_t auxssm_resample_killing_f64(void* stream, int64_t n_rows, int32_t N, const double* w,
                                     const double* u_kill, const double* u, int32_t* idx);
+int32_t auxssm_resample_systematic_f32(void* stream, int64_t n_rows, int32_t M, int32_t N, const float* w,
+                                       const float* u3, int32_t* idx);
+int32_t auxssm_resample_systematic_f64(void* stream, int64_t n_rows, int32_t M, int32_t N, const double* w,
+                                       const double* u3, int32_t* idx);
 int32_t auxssm_categorical_f32(void* stream, int64_t n_rows, int32_t N, const float* w, const float* u,
                                int32_t* idx);
 int32_t auxssm_categorical_f64(void* stream, int64_t n_rows, int32_t N, const double* w, const double* u,
                                int32_t* idx);
+
+/* ---- Host-side pieces of the samplers as kernels (no eager tensor arithmetic on the sweep path) ------------------
+ * grad_log_target  gradient at u[n_chains,T,d] of log M0(u_0) + G0(u_0) + sum_t [Gt(u_t) + log Mt(u_t | u_{t-1})]
+ *                  for the closed family set -- what the reference obtains with jax.grad(_log_pdf),
+ *                  csmc/independent.py:62,121-137.  Uses desc->{T,d,n_chains,potential,sig,ys_chain_stride}.
+ * cholesky         n lower Cholesky factors [n,d,d] with jnp.linalg.cholesky semantics (all-NaN factor on failure;
+ *                  d = 1 is a plain sqrt), the factorisations of the model constructors (auxiliary_csmc.py:18-19).
+ * delta_adaptation delta * exp(adaptation_rate (acc - target)), clipped to [min, max]            common.py:4-32
+ *                  (acc_stride 0: one acceptance rate shared by all n entries).
+ * mcmc_stats       running statistics of the outer loop, examples/stochastic_volatility/experiment.py:98-127:
+ *                  stats[c] = {n, acceptance mean, windowed acceptance (EMA with weight beta), mean squared jump};
+ *                  `updated` is int32 [n_chains, per_step].
+ * philox           counter-based Philox4x32-10 uniforms in (0,1) / Box-Muller normals (stand-in for jax.random):
+ *                  element stream = f(seed, *counter); *counter (device memory, may be NULL = 0) is incremented by
+ *                  one after the fill, so a captured CUDA graph draws fresh numbers on every replay.  Restated bit
+ *                  for bit (uniforms) in oracle/philox.py.                                                        */
+int32_t auxssm_csmc_grad_log_target_f32(void* stream, const auxssm_csmc_desc* desc, const float* u, const float* m0,
+                                        const float* chol_P0, const float* F, const float* b, const float* chol_Q,
+                                        const float* ys, float* grad);
+int32_t auxssm_csmc_grad_log_target_f64(void* stream, const auxssm_csmc_desc* desc, const double* u, const double* m0,
+                                        const double* chol_P0, const double* F, const double* b, const double* chol_Q,
+                                        const double* ys, double* grad);
+int32_t auxssm_cholesky_f32(void* stream, int64_t n, int32_t d, const float* A, float* L);
+int32_t auxssm_cholesky_f64(void* stream, int64_t n, int32_t d, const double* A, double* L);
+int32_t auxssm_delta_adaptation_f32(void* stream, int64_t n, const float* delta, const float* acc_rate,
+                                    int32_t acc_stride, double target_rate, double adaptation_rate, double min_delta,
+                                    double max_delta, float* delta_out);
+int32_t auxssm_delta_adaptation_f64(void* stream, int64_t n, const double* delta, const double* acc_rate,
+                                    int32_t acc_stride, double target_rate, double adaptation_rate, double min_delta,
+                                    double max_delta, double* delta_out);
+int32_t auxssm_mcmc_stats_f32(void* stream, int32_t n_chains, int64_t n_per_chain, int32_t per_step, const float* x_old,
+                              const float* x_new, const int32_t* updated, double beta, float* stats);
+int32_t auxssm_mcmc_stats_f64(void* stream, int32_t n_chains, int64_t n_per_chain, int32_t per_step,
+                              const double* x_old, const double* x_new, const int32_t* updated, double beta,
+                              double* stats);
+/* autocov: per-chain mean[n_chains] and biased autocovariances acov[n_chains, n] (double) of x[n_chains, n], the
+ * quantities examples/rare_event/ess.py:69-79 forms with an FFT (n <= ~28 000: one chain is held in shared memory). */
+int32_t auxssm_autocov_f32(void* stream, int32_t n_chains, int64_t n, const float* x, double* mean, double* acov);
+int32_t auxssm_autocov_f64(void* stream, int32_t n_chains, int64_t n, const double* x, double* mean, double* acov);
+int32_t auxssm_philox_uniform_f32(void* stream, uint64_t seed, uint64_t* counter, int64_t n, float* out);
+int32_t auxssm_philox_uniform_f64(void* stream, uint64_t seed, uint64_t* counter, int64_t n, double* out);
+int32_t auxssm_philox_normal_f32(void* stream, uint64_t seed, uint64_t* counter, int64_t n, float* out);
+int32_t auxssm_philox_normal_f64(void* stream, uint64_t seed, uint64_t* counter, int64_t n, double* out);
+int32_t auxssm_philox_advance(void* stream, uint64_t* counter, uint64_t by); /* *counter += by, on the stream */
 
 #ifdef __cplusplus
 }

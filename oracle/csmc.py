@@ -151,25 +151,33 @@ def killing(w, u_kill, u):
 
 
 def systematic(w, u, v, ww, N=None):
-    """Conditional systematic resampling (resamplings.py:40-86) for one weight vector and one
-    triple of uniforms (u, v, ww)."""
+    """Conditional systematic resampling (resamplings.py:40-86; Chopin & Singh Alg. 4) for one weight vector and
+    one triple of uniforms (u, v, ww).  All arithmetic in ``w.dtype``; the CDF is accumulated in the canonical
+    order shared with the kernels (the reference's ``jnp.cumsum`` order is unspecified).
+
+    ``searchsorted`` of an increasing grid gives a non-decreasing index vector, so the zeros of ``idx`` are its
+    first ``n_zero`` entries and ``zero_loc[k] = k`` (resamplings.py:81-84): the roll is by ``floor(n_zero * W)``.
+    """
     w = np.asarray(w)
+    dt = w.dtype.type
+    u, v, ww = dt(u), dt(v), dt(ww)
     M = w.shape[0]
     N = M if N is None else N
-    tmp = N * w[0]
+    cdf = canonical_cdf(w)
+    tmp = dt(N) * w[0]
     tmp_floor = np.floor(tmp)
     if tmp <= 1:
         uniform = tmp * u
     else:
         rem = tmp - tmp_floor
-        p_cond = rem * (tmp_floor + 1) / tmp
-        uniform = rem * u if v < p_cond else rem + (1.0 - rem) * u
-    linspace = (np.arange(N, dtype=w.dtype) + uniform) / N
-    idx = np.searchsorted(np.cumsum(w), linspace)
+        p_cond = rem * (tmp_floor + dt(1)) / tmp
+        uniform = rem * u if v < p_cond else rem + (dt(1) - rem) * u
+    linspace = (np.arange(N, dtype=w.dtype) + uniform) / dt(N)
+    idx = _search_left(cdf, linspace)
     n_zero = int(np.sum(idx == 0))
     zero_loc = np.flatnonzero(idx == 0)
     if n_zero != 1:
-        roll_idx = int(np.floor(n_zero * ww))
+        roll_idx = int(np.floor(dt(n_zero) * ww))
         shift = zero_loc[roll_idx] if roll_idx < zero_loc.shape[0] else -1
         idx = np.roll(idx, -shift)
     return np.clip(idx, 0, M - 1)
@@ -383,6 +391,8 @@ def csmc_forward(fk, x_star, normals, u_resample, resampling="multinomial", u_ki
             A = multinomial(w, u_resample[t - 1])
         elif resampling == "killing":
             A = killing(w, u_kill[t - 1], u_resample[t - 1])
+        elif resampling == "systematic":  # u_resample is [T-1, 3]: (U, V, W) of resamplings.py:65
+            A = systematic(w, *u_resample[t - 1])
         else:
             raise ValueError(resampling)
         x_prev = x[A]

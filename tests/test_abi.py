@@ -26,7 +26,7 @@ def test_exports_every_declared_symbol(lib):
     assert declared == set(_lib.exported_symbols())
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.auxssm_version() == 100
+    assert lib.auxssm_version() == 200
 
 
 def test_descriptor_validation_without_gpu(lib):

@@ -109,7 +109,9 @@ def compare(state, hist, oracle_out, dtype, C, u_res=None):
         npt.assert_array_equal(gB, B, err_msg="backward ancestors, chain %d" % c)
         npt.assert_array_equal(host(state.updated[c]), upd)
         npt.assert_allclose(host(state.x[c]), x, rtol=r, atol=r * np.abs(x).max())
-    assert full >= (C if dtype == torch.float64 else 1), "too few chains matched end to end (%d of %d)" % (full, C)
+    # fp64: every chain; fp32: at least half of the chains (rounded up) must match the oracle end to end -- the others
+    # stopped at a VERIFIED near-tie flip above (probability ~3e-5 per draw at N = 1024, i.e. ~0.15 per chain there)
+    assert full >= (C if dtype == torch.float64 else (C + 1) // 2), "too few chains matched end to end (%d of %d)" % (full, C)
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
@@ -171,7 +173,7 @@ def test_auxiliary_sweeps_vs_oracle(dtype, kind, d, N, T, backward):
         else:
             grad = None
             if kind == "independent-grad":
-                grad = host(csmc.grad_log_target(dev(u[None], dtype), M0, G0, Mt, Gt))[0].astype(npd)
+                grad = oc.grad_log_target(model, u).astype(npd)  # the oracle's own analytic gradient
             fk = oc.IndependentAuxFK(model, u, s, grad, gradient=(kind == "independent-grad"))
         want.append(oc.csmc_kernel(fk, model, x_star[c], normals[c], u_res[c], u_bwd[c], backward))
     if kind == "guided":
@@ -201,6 +203,7 @@ def test_grad_log_target_matches_finite_differences():
         return out
 
     g = host(csmc.grad_log_target(dev(u[None], torch.float64), M0, G0, Mt, Gt))[0]
+    npt.assert_allclose(g, oc.grad_log_target(model, u), rtol=1e-10, atol=1e-12)
     fd = np.zeros_like(u)
     for idx in np.ndindex(*u.shape):
         e = np.zeros_like(u)
@@ -240,7 +243,5 @@ def test_api_errors_mirror_the_reference():
         csmc.get_generic_kernel(csmc.independent_factory(M0, G, Mt, G), 8, backward=True, Pt=None)
     with pytest.raises(ValueError):  # csmc.py:49-50
         csmc.get_kernel(M0, G, Mt, G, 8, backward=True, Pt=object())
-    with pytest.raises(NotImplementedError):
-        csmc.get_independent_kernel(M0, G, Mt, G, 8, parallel=True)
     with pytest.raises(NotImplementedError):
         csmc.get_kernel(object(), G, Mt, G, 8)

@@ -145,7 +145,7 @@ def test_sampling_vs_oracle(dtype, d, T, C, chunks):
                          chunks > 1, time_chunks=chunks)
     torch.cuda.synchronize()
     r = TOL[dtype]["rtol"]
-    npt.assert_allclose(host(xs), exs, rtol=r, atol=r * max(1.0, np.abs(exs).max()) * (10 if dtype == torch.float32 else 1))
+    npt.assert_allclose(host(xs), exs, rtol=r, atol=r * max(1.0, np.abs(exs).max()))
 
 
 def test_sampling_zero_covariance_last_step():
@@ -209,7 +209,7 @@ def test_sv_sweep_vs_oracle(dtype, order, seed, parallel, dense_R):
     assert margin > 1e-3, "degenerate test draw"
     npt.assert_array_equal(host(state.updated).astype(bool), eacc)
     r = TOL[dtype]["rtol"]
-    npt.assert_allclose(host(state.x), ex, rtol=r, atol=r * np.abs(ex).max() * 10)
+    npt.assert_allclose(host(state.x), ex, rtol=r, atol=r * np.abs(ex).max())
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
@@ -297,5 +297,4 @@ def test_sampling_time_invariant_diagonal_F(dtype, d, T, C):
     for hint in (False, True):
         xs = kalman.sampling(dev(eps, dtype), dev(ms, dtype), dev(Ps, dtype), glg, False, f_diagonal=hint)
         r = TOL[dtype]["rtol"]
-        npt.assert_allclose(host(xs), exs, rtol=r,
-                            atol=r * max(1.0, np.abs(exs).max()) * (10 if dtype == torch.float32 else 1))
+        npt.assert_allclose(host(xs), exs, rtol=r, atol=r * max(1.0, np.abs(exs).max()))
