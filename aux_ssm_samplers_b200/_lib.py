@@ -47,6 +47,11 @@ class CsmcDesc(ctypes.Structure):
     ]
 
 
+class SweepDesc(ctypes.Structure):
+    _fields_ = [("lg", LgssmDesc), ("order", ctypes.c_int32), ("potential", ctypes.c_int32),
+                ("delta_stride", ctypes.c_int32), ("sig", ctypes.c_double), ("ys_chain_stride", ctypes.c_int64)]
+
+
 PROP_BOOTSTRAP, PROP_INDEPENDENT, PROP_GUIDED = 0, 1, 2
 POT_FLAT, POT_GAUSSIAN, POT_SV = 0, 1, 2
 RESAMPLE_MULTINOMIAL, RESAMPLE_KILLING, RESAMPLE_SYSTEMATIC = 0, 1, 2
@@ -68,6 +73,8 @@ _SIGNATURES = {
     "auxssm_kalman_sample_{s}": (_I32, [_P, _DESC] + [_P] * 7 + [_P, _SZ]),
     "auxssm_lgssm_logpdf_scratch_bytes": (_SZ, [_DESC, _I32]),
     "auxssm_lgssm_logpdf_{s}": (_I32, [_P, _DESC, _U32] + [_P] * 12 + [_P, _SZ]),
+    "auxssm_kalman_sweep_scratch_bytes": (_SZ, [ctypes.POINTER(SweepDesc), _I32]),
+    "auxssm_kalman_sweep_{s}": (_I32, [_P, ctypes.POINTER(SweepDesc)] + [_P] * 14 + [_P, _SZ]),
     "auxssm_auxiliary_draw_{s}": (_I32, [_P, _I64, _I64, _P, _P, _P, _I32, _P]),
     "auxssm_kalman_mh_{s}": (_I32, [_P, _I64, _I64, _P, _I32] + [_P] * 10),
     "auxssm_sv_obs_factory_{s}": (_I32, [_P, _I32, _I64, _I64, _I32, _P, _I64, _P, _P, _P, _I32, _P, _P, _I32]),

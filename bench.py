@@ -43,7 +43,7 @@ CSMC_CFG = {
     "configs[3]": dict(d=30, N=256, T=1024, chains_per_gpu=1024, kind="guided", resampling="killing", backward=True,
                        delta=0.1, what="guided auxiliary cSMC, killing resampling, d=30 SV, N=256, T=1024"),
 }
-CFG5 = dict(d=64, T=2048, chains_total=8192, order=1, delta=0.05, sub_batch=256)
+CFG5 = dict(d=64, T=2048, chains_total=8192, order=1, delta=0.05, sub_batch=1024)  # P_t history: 34 GB per sub-batch
 
 
 def make_data(d, T, seed):
@@ -585,7 +585,7 @@ def config5_leg(ctx, args):
     base = to(xs_true)
     # chain states live on the device as one [mine, T, d] array (4.3 GB for 8192 chains); sweeps go sub-batch by sub-batch
     x = base[None] + 0.3 * key.normal((mine, T, d), dtype, device)
-    n_sweeps = 2
+    n_sweeps = 3
     tracked = torch.empty((mine, 2, n_sweeps + 1), dtype=dtype, device=device)
     tracked[:, :, 0] = torch.stack([x[:, 0, 0], x[:, -1, 0]], dim=1)
 
@@ -624,42 +624,69 @@ def config5_leg(ctx, args):
 
 
 def few_chain_leg(ctx, args):
-    """The launch-bound regime of configs[0] (d=2, T=128, ONE chain, fp64, parallel-in-time): sweeps issued one by
-    one from the host vs n_inner sweeps + statistics + step-size adaptation replayed as one CUDA graph."""
+    """BASELINE configs[0] / SURVEY 8(d) cfg1: linear-Gaussian SSM, d = 2, T = 128, ONE chain, fp64, time-varying dense
+    F_t, auxiliary Kalman sampler with the parallel-in-time scans.  Three ways to issue the same sweep:
+    composed from the per-primitive entry points (~40 launches), the fused one-launch sweep issued from the host,
+    and n_inner fused sweeps + statistics + step-size adaptation replayed as ONE CUDA graph."""
     torch = ctx.torch
-    from aux_ssm_samplers_b200 import _lib, mcmc
+    from aux_ssm_samplers_b200 import _lib, latent_gaussian as lgm, mcmc
     from aux_ssm_samplers_b200 import stochastic_volatility as sv
     from aux_ssm_samplers_b200.draws import PhiloxDraws
     from aux_ssm_samplers_b200.kalman import KalmanSampler
     device = ctx.device
-    d, T = 2, 128
+    d, T, delta = 2, 128, 0.5
     dtype = torch.float64
-    (m0, P0, F, Q, b), xs_true, ys = make_data(d, T, 20250001)
+    rng = np.random.default_rng(20250001)
+    Fs = 0.9 * np.eye(d) + 0.1 * rng.standard_normal((T - 1, d, d)) / np.sqrt(d)
+    A = rng.standard_normal((T - 1, d, 5 * d))
+    Qs = A @ np.swapaxes(A, -1, -2) / (5 * d)
+    bs = rng.standard_normal((T - 1, d))
+    m0, P0 = np.zeros(d), np.eye(d)
+    x = np.zeros((1, T, d))
+    x[0, 0] = rng.standard_normal(d)
+    for t in range(1, T):
+        x[0, t] = Fs[t - 1] @ x[0, t - 1] + bs[t - 1] + np.linalg.cholesky(Qs[t - 1]) @ rng.standard_normal(d)
     to = lambda a: torch.as_tensor(np.asarray(a), dtype=dtype, device=device)
-    _, kernel = sv.get_kernel(to(ys), to(m0), to(P0), to(F), to(Q), to(b), parallel=True, order=2)
-    x0 = to(xs_true[None])
+    _, kernel = lgm.get_kernel(None, to(m0), to(P0), to(Fs), to(Qs), to(bs), True, 1, "flat")
     key = PhiloxDraws(1, device)
-    box = {"st": KalmanSampler(x0, True)}
+    box = {"st": KalmanSampler(to(x), True)}
     n0 = _lib.launch_count()
-    box["st"] = kernel(key, box["st"], 0.5)
+    box["st"] = kernel(key, box["st"], delta)
     per_sweep = _lib.launch_count() - n0
 
     def eager(i):
-        box["st"] = kernel(key, box["st"], 0.5)
+        box["st"] = kernel(key, box["st"], delta)
 
     for i in range(3):
         eager(i)
     ms_eager = ctx.timed(eager, 50)
-    n_inner = 16
-    loop = mcmc.DeviceLoop(kernel, PhiloxDraws(2, device), KalmanSampler(x0, True), 0.5, n_inner=n_inner)
+    n_inner = 32
+    loop = mcmc.DeviceLoop(kernel, PhiloxDraws(2, device), KalmanSampler(to(x), True), delta, n_inner=n_inner, adapt=True)
     loop.run(2)
     ms_graph = ctx.timed(lambda i: loop.run(1), 10) / n_inner
-    return {"config": "configs[0]-like: SV d=2, T=128, 1 chain, fp64, second-order aux-Kalman sweep, parallel-in-time",
-            "kernel_launches_per_sweep": int(per_sweep), "ms_per_sweep_host_issued": ms_eager,
-            "ms_per_sweep_cuda_graph": ms_graph, "sweeps_per_graph_replay": n_inner,
-            "kernel_launches_per_replay": int(loop.launches_per_replay),
-            "value": T / (ms_graph * 1e-3), "unit": UNIT,
-            "note": "graph = n_inner x (sweep + running statistics + delta adaptation), one host launch per replay"}
+    # the same regime composed from the per-primitive entry points (round-1 path): SV d=2 model, parallel-in-time
+    (m0s, P0s, Fsv, Qsv, bsv), xs_true, ys = make_data(d, T, 20250001)
+    _, kern_c = sv.get_kernel(to(ys), to(m0s), to(P0s), to(Fsv), to(Qsv), to(bsv), parallel=True, order=2)
+    boxc = {"st": KalmanSampler(to(xs_true[None]), True)}
+    n0 = _lib.launch_count()
+    boxc["st"] = kern_c(key, boxc["st"], 0.5)
+    per_sweep_c = _lib.launch_count() - n0
+
+    def composed(i):
+        boxc["st"] = kern_c(key, boxc["st"], 0.5)
+
+    for i in range(3):
+        composed(i)
+    ms_comp = ctx.timed(composed, 50)
+    return {"config": "configs[0]: LG-SSM d=2, T=128, 1 chain, fp64, time-varying dense F_t, aux-Kalman sweep, parallel scans",
+            "fused": {"kernel_launches_per_sweep": int(per_sweep), "ms_per_sweep_host_issued": ms_eager,
+                      "ms_per_sweep_cuda_graph": ms_graph, "sweeps_per_graph_replay": n_inner,
+                      "kernel_launches_per_replay": int(loop.launches_per_replay),
+                      "note": "per sweep: 3 Philox fills (+ counter bumps) and ONE auxssm_kalman_sweep launch (warp-shuffle "
+                              "scans); the graph adds running statistics + delta adaptation per sweep"},
+            "composed": {"kernel_launches_per_sweep": int(per_sweep_c), "ms_per_sweep_host_issued": ms_comp,
+                         "note": "SV d=2 second-order sweep through filter / sampler / log-density entry points (chunked scan)"},
+            "value": T / (ms_graph * 1e-3), "unit": UNIT}
 
 
 def run_gpu(args):

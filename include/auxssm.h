@@ -279,6 +279,36 @@ int32_t auxssm_categorical_f32(void* stream, int64_t n_rows, int32_t N, const fl
 int32_t auxssm_categorical_f64(void* stream, int64_t n_rows, int32_t N, const double* w, const double* u,
                                int32_t* idx);
 
+/* ---- Fused auxiliary-Kalman MH sweep: replaces kernel(key, state, delta) of kalman/generic.py:53-106 in ONE kernel
+ * launch for a latent-Gaussian target  pi(x) ~ LGSSM prior (m0, P0, F_t, Q_t, b_t; strides in desc->lg, time-varying
+ * or stride 0) x prod_t exp(g(x_t; ys_t)),  g = FLAT | GAUSSIAN (sig) | SV  (AUXSSM_POT_*), with the first / second
+ * order observation factories of examples/stochastic_volatility/auxiliary_kalman.py:28-48.  Narrow states only
+ * (d <= 4; AUXSSM_ERR_UNSUPPORTED otherwise: compose the entry points above).  One thread per time step; the
+ * filter's associative scan (filtering.py:49-63), the sampler's reverse scan (sampling.py:28-32) and the reverse
+ * proposal's filter are single-pass scans: warp shuffles inside a warp, a warp of warp aggregates inside a CTA,
+ * decoupled look-back across the CTAs a long chain is split over (all CTAs must be co-resident).
+ * x, normals_aux, normals_eps: [n_chains, T, d]; uniforms: [n_chains]; delta: [n_chains] (delta_stride 1) or [1];
+ * outputs x_out [n_chains, T, d], accepted [n_chains], alpha [n_chains] (may be NULL).                          */
+typedef struct auxssm_sweep_desc {
+  auxssm_lgssm_desc lg;     /* T, dx, n_chains and the strides of m0, P0, Fs, Qs, bs are used                       */
+  int32_t order;            /* 1 or 2                                                                             */
+  int32_t potential;        /* AUXSSM_POT_*                                                                       */
+  int32_t delta_stride;     /* 0 or 1                                                                             */
+  double sig;               /* GAUSSIAN potential                                                                 */
+  int64_t ys_chain_stride;  /* 0: ys[T,d] shared; T*d: per chain                                                  */
+} auxssm_sweep_desc;
+size_t auxssm_kalman_sweep_scratch_bytes(const auxssm_sweep_desc* desc, int32_t elem_size);
+int32_t auxssm_kalman_sweep_f32(void* stream, const auxssm_sweep_desc* desc, const float* x, const float* m0,
+                                const float* P0, const float* Fs, const float* Qs, const float* bs, const float* ys,
+                                const float* normals_aux, const float* normals_eps, const float* uniforms,
+                                const float* delta, float* x_out, int32_t* accepted, float* alpha, void* scratch,
+                                size_t scratch_bytes);
+int32_t auxssm_kalman_sweep_f64(void* stream, const auxssm_sweep_desc* desc, const double* x, const double* m0,
+                                const double* P0, const double* Fs, const double* Qs, const double* bs,
+                                const double* ys, const double* normals_aux, const double* normals_eps,
+                                const double* uniforms, const double* delta, double* x_out, int32_t* accepted,
+                                double* alpha, void* scratch, size_t scratch_bytes);
+
 /* ---- Host-side pieces of the samplers as kernels (no eager tensor arithmetic on the sweep path) ------------------
  * grad_log_target  gradient at u[n_chains,T,d] of log M0(u_0) + G0(u_0) + sum_t [Gt(u_t) + log Mt(u_t | u_{t-1})]
  *                  for the closed family set -- what the reference obtains with jax.grad(_log_pdf),
