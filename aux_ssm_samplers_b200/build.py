@@ -87,5 +87,28 @@ def build_library(verbose=False, force=False):
     return LIB
 
 
+def build_xla_ffi(verbose=False):
+    """Builds libauxssm_xla.so (csrc/xla/xla_ffi.cc: one XLA FFI handler per entry point) next to libauxssm.so.
+    Needs jaxlib's headers (``jax.ffi.include_dir()``); returns None where JAX is not installed (this image)."""
+    try:
+        import jax.ffi
+        inc = jax.ffi.include_dir()
+    except Exception as e:  # noqa: BLE001
+        if verbose:
+            print("xla_ffi adapter skipped: jax.ffi is not importable here (%s)" % e)
+        return None
+    out = os.path.join(HERE, "libauxssm_xla.so")
+    cmd = ["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-I", inc, "-I", INCLUDE, "-I", "/usr/local/cuda/include",
+           os.path.join(CSRC, "xla", "xla_ffi.cc"), "-o", out, "-L", HERE, "-lauxssm", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("xla_ffi build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    if verbose:
+        print("libauxssm_xla.so built:", out)
+    return out
+
+
 if __name__ == "__main__":
     build_library(verbose=True, force="--force" in sys.argv)
+    if "--xla-ffi" in sys.argv:
+        build_xla_ffi(verbose=True)
