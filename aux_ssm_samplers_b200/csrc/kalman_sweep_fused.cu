@@ -906,7 +906,18 @@ static int launch_sweep(cudaStream_t st, SweepArgs<T>& a, void* scratch, size_t 
   a.n_tiles = p.n_tiles;
   a.tile_len = p.tile_len;
   if (cudaMemsetAsync(a.status, 0, p.status_bytes, st) != cudaSuccess) { set_error("%s: cudaMemsetAsync failed", who); return AUXSSM_ERR_LAUNCH; }
-  kern<<<(unsigned)grid, p.threads, smem, st>>>(a);
+  if (p.n_tiles > 1) {
+    // tiles of one chain wait for each other (look-back flags, accept decision): a COOPERATIVE launch makes the
+    // runtime guarantee that every CTA is resident (or refuse the launch) whatever else shares the GPU
+    void* kargs[] = {&a};
+    if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3((unsigned)grid), dim3(p.threads), kargs, smem, st) !=
+        cudaSuccess) {
+      set_error("%s: cooperative launch of %ld CTAs failed: %s", who, grid, cudaGetErrorString(cudaGetLastError()));
+      return AUXSSM_ERR_LAUNCH;
+    }
+  } else {
+    kern<<<(unsigned)grid, p.threads, smem, st>>>(a);
+  }
   AUXSSM_CHECK_LAUNCH("auxssm_kalman_sweep (kalman_sweep_fused_kernel)");
   return AUXSSM_OK;
 }

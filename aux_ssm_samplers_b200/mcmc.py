@@ -111,3 +111,4 @@ class DeviceLoop:
             else:
                 self._body()
         return self.make_state(self.x, self.updated)
+
