@@ -51,7 +51,8 @@ template <typename T> __device__ __forceinline__ T block_scan_excl(T v, T* red, 
 }
 
 template <typename T, int D, int PROP>
-__global__ void __launch_bounds__(256) csmc_multi_kernel(CsmcArgs<T> a) {
+// d = 1 (configs[2]): four CTAs per SM (64 registers) -- the in-kernel Philox path must not halve the occupancy
+__global__ void __launch_bounds__(256, (D == 1 && sizeof(T) == 4) ? 4 : 1) csmc_multi_kernel(CsmcArgs<T> a) {
   constexpr int PPT = 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const auxssm_csmc_desc& dsc = a.d;

@@ -33,8 +33,8 @@ __device__ __forceinline__ double philox_u01(uint32_t a, uint32_t b) {
 
 enum { PHILOX_UNIFORM = 0, PHILOX_NORMAL = 1 };
 
-// all PER values of one block
-__device__ __forceinline__ void philox_block(int mode, uint64_t seed, uint64_t call, uint64_t blk, float (&v)[4]) {
+// all PER values of one block (not inlined: the sweep kernels call it from register-tight loops)
+static __device__ __noinline__ void philox_block(int mode, uint64_t seed, uint64_t call, uint64_t blk, float (&v)[4]) {
   uint32_t c[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)call, (uint32_t)(call >> 32)};
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
   const float a0 = philox_u01(c[0]), a1 = philox_u01(c[1]), a2 = philox_u01(c[2]), a3 = philox_u01(c[3]);
@@ -48,7 +48,7 @@ __device__ __forceinline__ void philox_block(int mode, uint64_t seed, uint64_t c
     v[0] = r0 * c0; v[1] = r0 * s0; v[2] = r1 * c1; v[3] = r1 * s1;
   }
 }
-__device__ __forceinline__ void philox_block(int mode, uint64_t seed, uint64_t call, uint64_t blk, double (&v)[2]) {
+static __device__ __noinline__ void philox_block(int mode, uint64_t seed, uint64_t call, uint64_t blk, double (&v)[2]) {
   uint32_t c[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)call, (uint32_t)(call >> 32)};
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
   const double a0 = philox_u01(c[0], c[1]), a1 = philox_u01(c[2], c[3]);
