@@ -81,6 +81,8 @@ _SIGNATURES = {
     "auxssm_sv_log_potential_{s}": (_I32, [_P, _I64, _I64, _P, _I64, _P, _P, _I32]),
     "auxssm_csmc_scratch_bytes": (_SZ, [ctypes.POINTER(CsmcDesc), _I32]),
     "auxssm_csmc_sweep_{s}": (_I32, [_P, ctypes.POINTER(CsmcDesc)] + [_P] * 21 + [_P, _SZ]),
+    "auxssm_pit_csmc_scratch_bytes": (_SZ, [ctypes.POINTER(CsmcDesc), _I32]),
+    "auxssm_pit_csmc_sweep_{s}": (_I32, [_P, ctypes.POINTER(CsmcDesc)] + [_P] * 14 + [_P, _SZ]),
     "auxssm_guided_gains_{s}": (_I32, [_P, _I32, _I32, _P, _P, _P, _P, _P]),
     "auxssm_normalize_{s}": (_I32, [_P, _I64, _I32, _P, _P]),
     "auxssm_resample_multinomial_{s}": (_I32, [_P, _I64, _I32, _P, _P, _P]),

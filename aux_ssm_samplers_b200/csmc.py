@@ -343,10 +343,85 @@ def get_independent_kernel(M0, G0, Mt, Gt, N, backward=False, Pt=None, gradient=
     """Auxiliary particle Gibbs with independent (separable) proposals (independent.py:18-75).
     ``gradient``: ``False`` / ``True`` (the reference's weights, see ``independent_factory``) / ``"per_particle"``."""
     if parallel:
-        raise NotImplementedError("parallel-in-time cSMC (independent.py:78-118, _primitives/csmc/pit) is out of "
-                                  "scope of this build (SURVEY section 8(f), rank 3)")
+        return _get_parallel_kernel(M0, G0, Mt, Gt, N, gradient)
     return get_generic_kernel(independent_factory(M0, G0, Mt, Gt, gradient), N, backward, Pt,
                               resampling=resampling, return_history=return_history)
+
+
+def pit_sweep(x_star, M0, Mt, pot, N, key, u, sqrt_half_delta, grad=None):
+    """One parallel-in-time cSMC sweep (``_primitives/csmc/pit/csmc.py:68-114``) with the independent auxiliary
+    proposals of independent.py:78-97: ``auxssm_pit_csmc_sweep_*``.  ``x_star, u [C,T,d]``, ``sqrt_half_delta [C,T]``,
+    ``grad [C,T,d]`` or None.  Draws: ``key.normal((C,T,N,d))`` then ``key.uniform((C,T,N))`` (row t: the stitch whose
+    right-hand block starts at t), or generated inside the kernels for an in-kernel Philox key."""
+    x = x_star.contiguous()
+    dev = _lib.require_cuda(x, u, sqrt_half_delta, grad)
+    dtype = x.dtype
+    C, T, d = x.shape
+    desc = CsmcDesc()
+    desc.T, desc.N, desc.d, desc.n_chains = T, N, d, C
+    desc.proposal, desc.potential, desc.sig = _lib.PROP_INDEPENDENT, pot.kind, float(pot.sig)
+    desc.gradient = 0 if grad is None else 1
+
+    def cvt(t):
+        if t is None:
+            return None
+        _lib.require_cuda(x, t)
+        return t.to(dtype=dtype).contiguous()
+
+    ys = None
+    if pot.ys is not None:
+        ys = cvt(pot.ys)
+        desc.ys_chain_stride = 0 if ys.dim() == 2 else T * d
+    u_, shd_, grad_ = cvt(u), cvt(sqrt_half_delta.expand(C, T)), cvt(grad)
+    in_kernel = bool(getattr(key, "in_kernel", False)) and hasattr(key, "counter")
+    if in_kernel:
+        normals = uniforms = None
+        desc.rng_seed = key.seed
+        desc.rng_counter_ptr = key.counter.data_ptr()
+    else:
+        normals = key.normal((C, T, N, d), dtype, dev).contiguous()
+        uniforms = key.uniform((C, T, N), dtype, dev).contiguous()
+    x_out = torch.empty_like(x)
+    anc = torch.empty((C, T), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    nbytes = L.auxssm_pit_csmc_scratch_bytes(desc, x.element_size())
+    if nbytes == 0:
+        _lib.check(-1, "auxssm_pit_csmc_scratch_bytes")
+    scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+    m0_, lp0_, f_, b_, lq_ = cvt(M0.m0), cvt(M0.chol_P0), cvt(Mt.F), cvt(Mt.b), cvt(Mt.chol_Q)
+    _lib.call("auxssm_pit_csmc_sweep_" + _lib.suffix(dtype), _lib.stream_ptr(dev), desc, _lib.ptr(x), _lib.ptr(m0_),
+              _lib.ptr(lp0_), _lib.ptr(f_), _lib.ptr(b_), _lib.ptr(lq_), _lib.ptr(ys), _lib.ptr(u_), _lib.ptr(shd_),
+              _lib.ptr(grad_), _lib.ptr(normals), _lib.ptr(uniforms), _lib.ptr(x_out), _lib.ptr(anc), _lib.ptr(scratch),
+              int(nbytes))
+    if in_kernel:
+        key.advance(2)
+    return x_out, anc
+
+
+def _get_parallel_kernel(M0, G0, Mt, Gt, N, gradient):
+    """``_get_parallel_kernel`` of independent.py:78-118: the parallel-in-time particle Gibbs kernel.
+    ``kernel(key, state, delta) -> CSMCState``; ``delta`` scalar, ``[T]`` or ``[C, T]``."""
+    pot = _check_family(M0, G0, Mt, Gt)
+    if gradient not in (False, True, 0, 1):
+        raise NotImplementedError("parallel=True supports gradient=False / True (independent.py:80-86)")
+
+    def kernel(key, state, delta):
+        x = state.x
+        squeeze = x.dim() == 2
+        xb = (x.unsqueeze(0) if squeeze else x).contiguous()
+        u, shd = _aux_u(key, xb, delta)                                       # independent.py:99-102
+        grad = grad_log_target(u, M0, G0, Mt, Gt) if gradient else None      # :81 (jax.grad(_log_pdf))
+        x_out, anc = pit_sweep(xb, M0, Mt, pot, N, key, u, shd, grad)
+        upd = anc != 0
+        if squeeze:
+            x_out, upd = x_out[0], upd[0]
+        return CSMCState(x=x_out, updated=upd)
+
+    def init(x):
+        T = x.shape[-2]
+        return CSMCState(x=x, updated=torch.zeros(x.shape[:-2] + (T,), dtype=torch.bool, device=x.device))
+
+    return init, kernel
 
 
 def guided_gains(P0, Q, sqrt_half_delta):

@@ -280,6 +280,20 @@ ffi::Error CsmcSweep(Call& c) {
                             D(c.opt(14)), D(c.opt(15)), DO(c.out(0)), I32(c.out(1)), nullptr, nullptr, nullptr, ws, nb)));
 }
 
+// operands: x_star, m0, chol_P0, F, b, chol_Q, ys, u, sqrt_half_delta, grad, normals, uniforms (empty = absent; both draw
+// arrays empty = in-kernel Philox);  results: x_out, ancestors
+ffi::Error PitCsmcSweep(Call& c) {
+  auxssm_csmc_desc d = CsmcDesc(c);
+  const size_t nb = auxssm_pit_csmc_scratch_bytes(&d, c.f64 ? 8 : 4);
+  void* ws = c.workspace(nb);
+  if (!c.err.empty()) return ffi::Error(ffi::ErrorCode::kInvalidArgument, c.err);
+  return Status(BOTH(
+      auxssm_pit_csmc_sweep_f32(c.stream, &d, F(c.in(0)), F(c.in(1)), F(c.in(2)), F(c.in(3)), F(c.in(4)), F(c.in(5)), F(c.opt(6)),
+                                F(c.in(7)), F(c.in(8)), F(c.opt(9)), F(c.opt(10)), F(c.opt(11)), FO(c.out(0)), I32(c.out(1)), ws, nb),
+      auxssm_pit_csmc_sweep_f64(c.stream, &d, D(c.in(0)), D(c.in(1)), D(c.in(2)), D(c.in(3)), D(c.in(4)), D(c.in(5)), D(c.opt(6)),
+                                D(c.in(7)), D(c.in(8)), D(c.opt(9)), D(c.opt(10)), D(c.opt(11)), DO(c.out(0)), I32(c.out(1)), ws, nb)));
+}
+
 // operands: u, m0, chol_P0, F, b, chol_Q, ys;  results: grad
 ffi::Error CsmcGradLogTarget(Call& c) {
   auxssm_csmc_desc d = CsmcDesc(c);
@@ -412,6 +426,7 @@ AUXSSM_FFI(kalman_sweep, KalmanSweep);
 AUXSSM_FFI(sv_obs_factory, SvObsFactory);
 AUXSSM_FFI(sv_log_potential, SvLogPotential);
 AUXSSM_FFI(csmc_sweep, CsmcSweep);
+AUXSSM_FFI(pit_csmc_sweep, PitCsmcSweep);
 AUXSSM_FFI(csmc_grad_log_target, CsmcGradLogTarget);
 AUXSSM_FFI(guided_gains, GuidedGains);
 AUXSSM_FFI(normalize, Normalize);

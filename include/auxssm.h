@@ -244,6 +244,29 @@ int32_t auxssm_csmc_sweep_f64(void* stream, const auxssm_csmc_desc* desc, const 
                               double* xs_hist, double* logw_hist, int32_t* anc_hist, void* scratch,
                               size_t scratch_bytes);
 
+/* ---- Parallel-in-time conditional SMC: replaces csmc/independent.py:78-118 (get_independent_kernel(...,
+ * parallel=True)) and _primitives/csmc/pit/{csmc.py:68-114, operator.py:39-149, dc_map.py:73-123} for the closed
+ * family above with INDEPENDENT proposals  x_t^n ~ N(u_t + s_t^2 grad_t, s_t^2 I)  (grad used when desc->gradient,
+ * which also switches the initial weights to log N(x; u_t, s_t) - log N(x; mean_t, s_t), pit/csmc.py:83-85).
+ * Uses desc->{T, N, d, n_chains, potential, gradient, sig, ys_chain_stride, rng_*}; N <= 128, d <= 32, T >= 2.
+ * Draws (parity mode): normals[n_chains,T,N,d] (pit/csmc.py:75) and uniforms[n_chains,T,N]: row t serves the stitch
+ * whose right-hand block starts at time t (keys_b[0], operator.py:78,81; the last level draws ONE pair from
+ * uniforms[.,t,0]).  Both NULL: generated in the kernels with Philox (call = rng_counter + 0 / + 1).
+ * log2(T) + 1 launches: every boundary (t-1, t) is stitched once, N^2 weights in shared memory, canonical
+ * log-sum-exp / CDF order, blocks of trajectories are index rows (`origins`, operator.py:97-99), never
+ * copied.  Outputs x_out[n_chains,T,d], ancestors[n_chains,T] (updated = ancestors != 0, pit/csmc.py:58).        */
+size_t auxssm_pit_csmc_scratch_bytes(const auxssm_csmc_desc* desc, int32_t elem_size);
+int32_t auxssm_pit_csmc_sweep_f32(void* stream, const auxssm_csmc_desc* desc, const float* x_star, const float* m0,
+                                  const float* chol_P0, const float* F, const float* b, const float* chol_Q,
+                                  const float* ys, const float* u, const float* sqrt_half_delta, const float* grad,
+                                  const float* normals, const float* uniforms, float* x_out, int32_t* ancestors,
+                                  void* scratch, size_t scratch_bytes);
+int32_t auxssm_pit_csmc_sweep_f64(void* stream, const auxssm_csmc_desc* desc, const double* x_star, const double* m0,
+                                  const double* chol_P0, const double* F, const double* b, const double* chol_Q,
+                                  const double* ys, const double* u, const double* sqrt_half_delta,
+                                  const double* grad, const double* normals, const double* uniforms, double* x_out,
+                                  int32_t* ancestors, void* scratch, size_t scratch_bytes);
+
 /* Gains of the guided proposal for every time step (auxiliary_guided_csmc.py:155-157, :44-46, :104-106):
  * K_t = P (P + s_t^2 I)^{-1}, chol_Lam_t = chol(sym(P - K_t P)) with non-finite entries replaced by
  * s_t I; P = P0 for t = 0 and Q otherwise.  sqrt_half_delta[T]; outputs [T,d,d].                       */

@@ -84,16 +84,17 @@ def _scan32(v):
 
 def canonical_cdf(w):
     """Inclusive prefix sum over the last axis in the kernels' order (dtype preserved): Hillis--Steele scan
-    inside groups of 32, the same scan over the (zero-padded) group totals gives the group offsets, one add
-    of the offset (group 0 is not offset).  Supports up to 1024 entries (32 groups), like the kernels."""
+    inside groups of 32, the canonical CDF of the (zero-padded) group totals -- the same rule, recursively -- gives
+    the group offsets, one add of the offset (group 0 is not offset).  Up to 1024 entries that is two levels (what
+    the particle kernels do with one thread per particle); the N^2 stitching weights of the parallel-in-time cSMC
+    need a third."""
     w = np.asarray(w)
     n = w.shape[-1]
-    assert n <= 1024
     v = _scan32(_pad32(w, 0).reshape(w.shape[:-1] + (-1, 32)))
     ng = v.shape[-2]
-    tot = _scan32(_pad32(v[..., 31], 0))[..., :ng]      # inclusive scan of the group totals
     out = v.copy()
     if ng > 1:
+        tot = canonical_cdf(v[..., 31])                 # inclusive canonical scan of the group totals
         out[..., 1:, :] = v[..., 1:, :] + tot[..., :-1, None]
     return out.reshape(w.shape[:-1] + (-1,))[..., :n]
 

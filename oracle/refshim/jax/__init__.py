@@ -1,6 +1,6 @@
 """NumPy-backed stand-in for the slice of `jax` the reference imports (TEST INFRASTRUCTURE; ../README.md)."""
 from ._core import jit, vmap, grad, value_and_grad, tree_map, JArray as Array  # noqa: F401
-from . import numpy, lax, random, scipy, tree_util  # noqa: F401
+from . import numpy, lax, random, scipy, tree_util, dtypes  # noqa: F401
 
 __version__ = "0.0-refshim"
 

@@ -406,6 +406,15 @@ def vmap(fun, in_axes=0, out_axes=0, **_kw):
         for i in range(n):
             sl = [a if ax is None else tree_map(lambda l: _slice_leaf(l, i, ax), a) for a, ax in zip(args, axes)]
             outs.append(fun(*sl))
+        if n == 0:
+            # empty batch (dc_map.py:104 passes an empty "unchanged" set through when T is a power of two): JAX
+            # returns outputs with a zero-length mapped axis; evaluate `fun` once on a placeholder element for shapes
+            def fake(l, ax):
+                shp = tuple(d for j, d in enumerate(np.shape(l)) if j != ax)
+                return wrap(np.zeros(shp, dtype=np.asarray(l).dtype))
+            sl = [a if ax is None else tree_map(lambda l, ax=ax: fake(l, ax), a) for a, ax in zip(args, axes)]
+            proto = fun(*sl)
+            return tree_map(lambda r: wrap(np.zeros((0,) + np.shape(r), dtype=np.asarray(r).dtype)), proto)
         res = tree_stack(outs)
         if out_axes != 0:
             res = tree_map(lambda l: linear(l, lambda a: np.moveaxis(a, 0, out_axes)), res)
