@@ -94,6 +94,8 @@ _SIGNATURES = {
     "auxssm_delta_adaptation_{s}": (_I32, [_P, _I64, _P, _P, _I32, _F64, _F64, _F64, _F64, _P]),
     "auxssm_mcmc_stats_{s}": (_I32, [_P, _I32, _I64, _I32, _P, _P, _P, _F64, _P]),
     "auxssm_autocov_{s}": (_I32, [_P, _I32, _I64, _P, _P, _P]),
+    "auxssm_sigma_points_{s}": (_I32, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
+    "auxssm_sigma_fit_{s}": (_I32, [_P, _I64, _I32, _I32, _I32] + [_P] * 6 + [_I64, _I64, _P, _P, _P]),
     "auxssm_philox_uniform_{s}": (_I32, [_P, _U64, _P, _I64, _P]),
     "auxssm_philox_normal_{s}": (_I32, [_P, _U64, _P, _I64, _P]),
     "auxssm_philox_advance": (_I32, [_P, _P, _U64]),

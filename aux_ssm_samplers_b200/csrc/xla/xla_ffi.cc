@@ -310,6 +310,24 @@ ffi::Error GuidedGains(Call& c) {
                      auxssm_guided_gains_f64(c.stream, Tn, d, D(c.in(0)), D(c.in(1)), D(c.in(2)), DO(c.out(0)), DO(c.out(1)))));
 }
 
+// operands: x_star [n,dx], P_star [n,dx,dx], xi [dx,n_pts];  results: points [n,n_pts,dx], chol [n,dx,dx]
+ffi::Error SigmaPoints(Call& c) {
+  const int64_t n = c.attr("n", 1);
+  const int32_t dx = (int32_t)c.attr("dx", 1), np = (int32_t)c.attr("n_pts", 1);
+  return Status(BOTH(auxssm_sigma_points_f32(c.stream, n, dx, np, F(c.in(0)), F(c.in(1)), F(c.in(2)), FO(c.out(0)), FO(c.out(1))),
+                     auxssm_sigma_points_f64(c.stream, n, dx, np, D(c.in(0)), D(c.in(1)), D(c.in(2)), DO(c.out(0)), DO(c.out(1)))));
+}
+
+// operands: w, points, x_star, chol, f_pts, v_pts;  results: F, Q, b
+ffi::Error SigmaFit(Call& c) {
+  const int64_t n = c.attr("n", 1), vis = c.attr("v_item_stride", 0), vps = c.attr("v_point_stride", 0);
+  const int32_t dx = (int32_t)c.attr("dx", 1), dy = (int32_t)c.attr("dy", 1), np = (int32_t)c.attr("n_pts", 1);
+  return Status(BOTH(auxssm_sigma_fit_f32(c.stream, n, dx, dy, np, F(c.in(0)), F(c.in(1)), F(c.in(2)), F(c.in(3)), F(c.in(4)), F(c.in(5)),
+                                          vis, vps, FO(c.out(0)), FO(c.out(1)), FO(c.out(2))),
+                     auxssm_sigma_fit_f64(c.stream, n, dx, dy, np, D(c.in(0)), D(c.in(1)), D(c.in(2)), D(c.in(3)), D(c.in(4)), D(c.in(5)),
+                                          vis, vps, DO(c.out(0)), DO(c.out(1)), DO(c.out(2)))));
+}
+
 // rows = product of the leading axes of operand 0, N = its last axis
 void RowsOf(Call& c, size_t i, int64_t& rows, int32_t& n) {
   std::vector<int64_t> dm = c.dims(i);
@@ -438,5 +456,7 @@ AUXSSM_FFI(cholesky, Cholesky);
 AUXSSM_FFI(delta_adaptation, DeltaAdaptation);
 AUXSSM_FFI(mcmc_stats, McmcStats);
 AUXSSM_FFI(autocov, Autocov);
+AUXSSM_FFI(sigma_points, SigmaPoints);
+AUXSSM_FFI(sigma_fit, SigmaFit);
 AUXSSM_FFI(philox_uniform, PhiloxUniform);
 AUXSSM_FFI(philox_normal, PhiloxNormal);

@@ -370,6 +370,26 @@ int32_t auxssm_mcmc_stats_f64(void* stream, int32_t n_chains, int64_t n_per_chai
  * quantities examples/rare_event/ess.py:69-79 forms with an FFT (n <= ~28 000: one chain is held in shared memory). */
 int32_t auxssm_autocov_f32(void* stream, int32_t n_chains, int64_t n, const float* x, double* mean, double* acov);
 int32_t auxssm_autocov_f64(void* stream, int32_t n_chains, int64_t n, const double* x, double* mean, double* acov);
+/* ---- Sigma-point linearisation: replaces _primitives/linearisation.py:110-139
+ * (_generic_sigma_points / _cov behind `cubature` :78-107 and `gauss_hermite` :48-75), batched over n items
+ * (chain x time step), split at the seam where the reference calls the user's `mean` / `cov` callables:
+ *   sigma_points  chol[n,dx,dx] = cholesky(P_star[n,dx,dx]);  points[n,n_pts,dx] = x_star + (chol xi)^T, xi[dx,n_pts]
+ *   (caller)      f_pts[n,n_pts,dy] = mean(points),  v_pts = cov(points)
+ *   sigma_fit     F[n,dy,dx], Q[n,dy,dy], b[n,dy] from the weights w[n_pts] and the values at the points.
+ *                 v_pts element (item i, point p) starts at v_pts + i*v_item_stride + p*v_point_stride
+ *                 (strides 0 = a covariance shared by all items / all points).        dx, dy <= 32.             */
+int32_t auxssm_sigma_points_f32(void* stream, int64_t n, int32_t dx, int32_t n_pts, const float* x_star,
+                                const float* P_star, const float* xi, float* points, float* chol);
+int32_t auxssm_sigma_points_f64(void* stream, int64_t n, int32_t dx, int32_t n_pts, const double* x_star,
+                                const double* P_star, const double* xi, double* points, double* chol);
+int32_t auxssm_sigma_fit_f32(void* stream, int64_t n, int32_t dx, int32_t dy, int32_t n_pts, const float* w,
+                             const float* points, const float* x_star, const float* chol, const float* f_pts,
+                             const float* v_pts, int64_t v_item_stride, int64_t v_point_stride, float* F, float* Q,
+                             float* b);
+int32_t auxssm_sigma_fit_f64(void* stream, int64_t n, int32_t dx, int32_t dy, int32_t n_pts, const double* w,
+                             const double* points, const double* x_star, const double* chol, const double* f_pts,
+                             const double* v_pts, int64_t v_item_stride, int64_t v_point_stride, double* F, double* Q,
+                             double* b);
 int32_t auxssm_philox_uniform_f32(void* stream, uint64_t seed, uint64_t* counter, int64_t n, float* out);
 int32_t auxssm_philox_uniform_f64(void* stream, uint64_t seed, uint64_t* counter, int64_t n, double* out);
 int32_t auxssm_philox_normal_f32(void* stream, uint64_t seed, uint64_t* counter, int64_t n, float* out);

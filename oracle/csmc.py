@@ -213,25 +213,35 @@ class LinearGaussianModel:
         self.dtype = dtype
         self.m0, self.P0, self.F, self.Q, self.b = [np.asarray(a, dtype=dtype) for a in (m0, P0, F, Q, b)]
         self.d = self.m0.shape[0]
-        self.cP0, self.cQ = chol(self.P0), chol(self.Q)
+        # time-varying dynamics: F [T-1, d, d], Q [T-1, d, d], b [T-1, d] -- the leading axis of `Mt.params`, which
+        # the reference scans over (csmc.py:103): entry t - 1 is the transition INTO time step t
+        self.time_varying = self.F.ndim == 3
+        self.cP0 = chol(self.P0)
+        self.cQ = np.stack([chol(q) for q in self.Q]) if self.time_varying else chol(self.Q)
         self.potential, self.sig = potential, dtype(sig)
         self.ys = None if ys is None else np.asarray(ys, dtype=dtype)
 
-    # prior pieces
+    def _dyn(self, t):
+        if not self.time_varying:
+            return self.F, self.b, self.cQ
+        return self.F[t - 1], self.b[t - 1], self.cQ[t - 1]
+
+    # prior pieces (t = the time step the transition leads INTO; ignored for time-invariant dynamics)
     def m0_sample(self, eps):
         return self.m0 + mv(self.cP0, eps)
 
     def m0_logpdf(self, x):
         return mvn_logpdf(x, self.m0, self.cP0)
 
-    def mt_mean(self, x):
-        return mv(self.F, x) + self.b
+    def mt_mean(self, x, t=None):
+        F, b, _ = self._dyn(t)
+        return mv(F, x) + b
 
-    def mt_sample(self, eps, x):
-        return self.mt_mean(x) + mv(self.cQ, eps)
+    def mt_sample(self, eps, x, t=None):
+        return self.mt_mean(x, t) + mv(self._dyn(t)[2], eps)
 
-    def mt_logpdf(self, x_new, x):
-        return mvn_logpdf(x_new, self.mt_mean(x), self.cQ)
+    def mt_logpdf(self, x_new, x, t=None):
+        return mvn_logpdf(x_new, self.mt_mean(x, t), self._dyn(t)[2])
 
     def pot(self, t, x):
         if self.potential == "flat":
@@ -277,7 +287,7 @@ class BootstrapFK:
         return self.m.pot(0, x)
 
     def mt_sample(self, t, eps, x_prev):
-        return self.m.mt_sample(eps, x_prev)
+        return self.m.mt_sample(eps, x_prev, t)
 
     def gt(self, t, x, x_prev):
         return self.m.pot(t, x)
@@ -323,7 +333,7 @@ class IndependentAuxFK:
         return self.m.pot(0, x) + self.m.m0_logpdf(x) + self._corr(0, x)
 
     def gt(self, t, x, x_prev):
-        return self.m.mt_logpdf(x, x_prev) + self.m.pot(t, x) + self._corr(t, x)
+        return self.m.mt_logpdf(x, x_prev, t) + self.m.pot(t, x) + self._corr(t, x)
 
 
 class GuidedAuxFK:
@@ -416,7 +426,8 @@ def backward_scanning_pass(u_T, w_T, xs, As):
 
 
 def backward_sampling_pass(model, u_backward, w_T, xs, log_ws):
-    """Backward sampling (csmc.py:127-149) with ``Pt.logpdf`` = the model's transition density.
+    """Backward sampling (csmc.py:127-149) with ``Pt.logpdf`` = the transition density of ``model`` (the prior model,
+    or a different ``Pt`` model: csmc.py:47-50).
     ``u_backward[0]`` draws B_T (keys[0]); ``u_backward[k]`` serves time T-1-k (keys[1:] scanned over
     the reversed history)."""
     T = xs.shape[0]
@@ -426,7 +437,7 @@ def backward_sampling_pass(model, u_backward, w_T, xs, log_ws):
     B[-1] = categorical(w_T, np.asarray(u_backward[0]))
     x[-1] = xs[-1, B[-1]]
     for k, t in enumerate(range(T - 2, -1, -1)):
-        lw = np.asarray(model.mt_logpdf(x[t + 1], xs[t]), dtype=dtype) + log_ws[t]
+        lw = np.asarray(model.mt_logpdf(x[t + 1], xs[t], t + 1), dtype=dtype) + log_ws[t]
         w = normalize(lw)
         B[t] = categorical(w, np.asarray(u_backward[k + 1]))
         x[t] = xs[t, B[t]]
@@ -434,11 +445,12 @@ def backward_sampling_pass(model, u_backward, w_T, xs, log_ws):
 
 
 def csmc_kernel(fk, model, x_star, normals, u_resample, u_backward, backward, resampling="multinomial",
-                u_kill=None):
-    """``kernel`` (csmc.py:52-59) for one chain: returns (x [T,d], updated [T], ancestors [T], history)."""
+                u_kill=None, pt_model=None):
+    """``kernel`` (csmc.py:52-59) for one chain: returns (x [T,d], updated [T], ancestors [T], history).
+    ``pt_model``: the model whose transition density is ``Pt.logpdf`` in the backward pass (default: ``model``)."""
     w_T, xs, log_ws, As = csmc_forward(fk, x_star, normals, u_resample, resampling, u_kill)
     if backward:
-        x, B = backward_sampling_pass(model, u_backward, w_T, xs, log_ws)
+        x, B = backward_sampling_pass(model if pt_model is None else pt_model, u_backward, w_T, xs, log_ws)
     else:
         x, B = backward_scanning_pass(u_backward[0], w_T, xs, As)
     return x, B != 0, B, (w_T, xs, log_ws, As)
