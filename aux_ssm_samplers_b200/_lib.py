@@ -44,6 +44,8 @@ class CsmcDesc(ctypes.Structure):
         ("backward", ctypes.c_int32), ("gradient", ctypes.c_int32),
         ("ys_chain_stride", ctypes.c_int64), ("gains_time_stride", ctypes.c_int64), ("sig", ctypes.c_double),
         ("rng_seed", ctypes.c_uint64), ("rng_counter", ctypes.c_uint64), ("rng_counter_ptr", ctypes.c_void_p),
+        ("dyn_time_varying", ctypes.c_int32), ("pt_F", ctypes.c_void_p), ("pt_b", ctypes.c_void_p),
+        ("pt_chol_Q", ctypes.c_void_p),
     ]
 
 

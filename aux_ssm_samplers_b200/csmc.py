@@ -80,12 +80,18 @@ class GaussianDistribution(Distribution, UnivariatePotential):
 
 
 class LinearGaussianDynamics(Dynamics):
-    """x_t ~ N(F x_{t-1} + b, Q), time-invariant (``Mt`` of auxiliary_csmc.py:33-40; ``GaussianDynamics(rho)``
-    of the reference's tests is F = rho, Q = 1 - rho^2, b = 0)."""
+    """x_t ~ N(F x_{t-1} + b, Q) (``Mt`` of auxiliary_csmc.py:33-40; ``GaussianDynamics(rho)`` of the reference's
+    tests is F = rho, Q = 1 - rho^2, b = 0).  Time-invariant ``F [d,d], Q [d,d], b [d]``, or time-varying
+    ``F [T-1,d,d], Q [T-1,d,d], b [T-1,d]`` -- the leading axis of the reference's ``Mt.params``, scanned over t
+    (csmc.py:103): entry t - 1 is the transition into time step t."""
 
     def __init__(self, F, Q, b):
         self.F, self.Q, self.b = F, Q, b
+        self.time_varying = F.dim() == 3
+        if self.time_varying and not (Q.dim() == 3 and b.dim() == 2 and Q.shape[0] == F.shape[0] == b.shape[0]):
+            raise ValueError("time-varying dynamics need F [T-1,d,d], Q [T-1,d,d] and b [T-1,d]")
         self.chol_Q = cholesky(Q)
+        self.params = (F, b, self.chol_Q) if self.time_varying else None
 
     def logpdf(self, x_t_p_1, x_t, params):
         raise NotImplementedError("evaluated inside the fused kernel")
@@ -149,7 +155,7 @@ def _check_family(M0, G0, Mt, Gt):
     return Gt
 
 
-def _sweep(x_star, M0, Mt, pot, N, backward, resampling, key, aux=None, return_history=False):
+def _sweep(x_star, M0, Mt, pot, N, backward, resampling, key, aux=None, return_history=False, Pt=None):
     squeeze = x_star.dim() == 2
     x = x_star.unsqueeze(0) if squeeze else x_star
     x = x.contiguous()
@@ -173,6 +179,16 @@ def _sweep(x_star, M0, Mt, pot, N, backward, resampling, key, aux=None, return_h
         _lib.require_cuda(x, t)
         return t.to(dtype=dtype).contiguous()
 
+    if Mt.time_varying:
+        if Mt.F.shape[0] != T - 1:
+            raise AuxssmError("time-varying dynamics carry T - 1 = %d transitions, got %d" % (T - 1, Mt.F.shape[0]))
+        desc.dyn_time_varying = 1
+    ptf_ = ptb_ = ptq_ = None
+    if backward and Pt is not None and Pt is not Mt:  # csmc.py:47-50: Pt.logpdf drives the backward weights
+        if Pt.time_varying != Mt.time_varying or Pt.F.shape != Mt.F.shape:
+            raise AuxssmError("Pt must have the same (time-varying or not) layout as Mt")
+        ptf_, ptb_, ptq_ = cvt(Pt.F), cvt(Pt.b), cvt(Pt.chol_Q)
+        desc.pt_F, desc.pt_b, desc.pt_chol_Q = ptf_.data_ptr(), ptb_.data_ptr(), ptq_.data_ptr()
     ys = None
     if pot.ys is not None:
         ys = cvt(pot.ys)
@@ -233,11 +249,11 @@ def get_kernel(M0, G0, Mt, Gt, N, backward=False, Pt=None, *, resampling="multin
     elif backward and not hasattr(Pt, "logpdf"):
         raise ValueError("When `backward` is True, `Pt` must implement a valid logpdf method.")
     pot = _check_family(M0, G0, Mt, Gt)
-    if backward and Pt is not Mt and not (isinstance(Pt, LinearGaussianDynamics) and Pt.F is Mt.F and Pt.Q is Mt.Q):
-        raise NotImplementedError("backward sampling uses the prior transition of the fused family (Pt must be Mt)")
+    if backward and Pt is not Mt and not isinstance(Pt, LinearGaussianDynamics):
+        raise NotImplementedError("backward sampling needs a LinearGaussianDynamics `Pt` (closed family set)")
 
     def kernel(key, state):
-        return _sweep(state.x, M0, Mt, pot, N, backward, resampling, key, _aux, return_history)
+        return _sweep(state.x, M0, Mt, pot, N, backward, resampling, key, _aux, return_history, Pt if backward else None)
 
     def init(x_star):
         T = x_star.shape[-2]

@@ -95,6 +95,10 @@ static int csmc_entry(void* stream, const auxssm_csmc_desc* d, const T* x_star, 
     set_error("%s: killing resampling needs u_kill", who);
     return AUXSSM_ERR_INVALID;
   }
+  if (d->dyn_time_varying && (d->proposal == AUXSSM_PROP_GUIDED || d->gradient != 0)) {
+    set_error("%s: time-varying dynamics are supported for BOOTSTRAP and INDEPENDENT (gradient = 0) proposals", who);
+    return AUXSSM_ERR_UNSUPPORTED;
+  }
   const bool full_hist = xs_hist && lw_hist && a_hist;
   if (!full_hist && (xs_hist || lw_hist || a_hist)) {
     set_error("%s: pass all three history outputs or none", who);

@@ -408,7 +408,26 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
   m.s_t = T(1);
   __syncthreads();
 
+  // Time-varying dynamics (Mt.params scanned over t, csmc.py:103) and a separate backward model Pt (csmc.py:47-50):
+  // the shared-memory image of (F, b, chol Q) is reloaded at the steps where it changes.
+  const bool tv = dsc.dyn_time_varying != 0;
+  const T* ptF = dsc.pt_F ? static_cast<const T*>(dsc.pt_F) : a.F;
+  const T* ptb = dsc.pt_b ? static_cast<const T*>(dsc.pt_b) : a.b;
+  const T* ptLq = dsc.pt_chol_Q ? static_cast<const T*>(dsc.pt_chol_Q) : a.Lq;
+  const bool pt_differs = dsc.backward && (dsc.pt_F || dsc.pt_b || dsc.pt_chol_Q);
+  auto load_dynamics = [&](const T* Fg, const T* bg, const T* Lg, int idx) {  // all threads; ends with a barrier
+    const int64_t o2 = tv ? (int64_t)idx * d * d : 0, o1 = tv ? (int64_t)idx * d : 0;
+    __syncthreads();
+    load_padded<T, D>(Fg + o2, m.F, d);
+    load_padded<T, D>(Lg + o2, m.Lq, d);
+    if (i < D) m.b[i] = (i < d) ? bg[o1 + i] : T(0);
+    __syncthreads();
+    m.cst_q = factor_consts<T, D>(m.Lq, m.invq, d);
+    __syncthreads();
+  };
+
   for (int c = blockIdx.x; c < dsc.n_chains; c += gridDim.x) {
+    if (pt_differs && !tv && c != (int)blockIdx.x) load_dynamics(a.F, a.b, a.Lq, 0);  // the last chain left Pt behind
     const int64_t hs = a.hist_per_chain ? c : blockIdx.x;  // history slot
     T* xs_h = a.xs_hist + hs * (int64_t)Tn * N * d;
     T* lw_h = a.lw_hist + hs * (int64_t)Tn * N;
@@ -473,6 +492,7 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
 #pragma unroll
         for (int k = 0; k < D; ++k) if (k < d) xp[k] = part[anc * d + k];
       }
+      if (tv && !first) load_dynamics(a.F, a.b, a.Lq, t - 1);  // parents are in registers; `part` is not touched
       // (3) per-step parameters -> shared (read after the barrier below)
       if (i < D) {
         m.xs_t[i] = xs_c;
@@ -554,11 +574,13 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
     }
     if (dsc.backward) {
       T ub_n = (Tn > 1) ? a.draw_u_bwd(ub + 1) : T(0);
+      if (pt_differs && !tv && Tn > 1) load_dynamics(ptF, ptb, ptLq, 0);
       for (int t = Tn - 2, k2 = 1; t >= 0; --t, ++k2) {
         T xt[D], xpred[D], xsel[D];
         T lwh = T(0);
         const T ub_c = ub_n;
         if (t > 0) ub_n = a.draw_u_bwd(ub + k2 + 1);
+        if (tv && (pt_differs || t < Tn - 2)) load_dynamics(ptF, ptb, ptLq, t);  // Pt(x_{t+1} | x_t): entry t
         {
           // history of step t, staged with coalesced loads
           const T* xg = xs_h + (int64_t)t * N * d;

@@ -40,7 +40,8 @@ template <typename T, int PROP>
 int launch_csmc_family(cudaStream_t st, CsmcArgs<T>& a, int max_slots, int* slots_used) {
   const int d = a.d.d, N = a.d.N;
   const bool big = N > 256;
-  {
+  const bool general_dynamics = a.d.dyn_time_varying != 0 || a.d.pt_F || a.d.pt_b || a.d.pt_chol_Q;
+  if (!general_dynamics) {  // the two re-decomposed kernels hold a time-invariant model with Pt = Mt
     const int rc = launch_csmc_wide_family<T, PROP>(st, a, max_slots, slots_used);
     if (rc != AUXSSM_WIDE_NA) return rc;
   }

@@ -190,6 +190,19 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
   T* fd = p; p += D;  // diag(F) (LEAN)
   s.dg = p;
   constexpr bool PAD = LEAN && (D <= 32);
+  // D = 64: P_{t+1} is staged by the TMA unit (one cp.async.bulk per 256-byte row, completed on an mbarrier) into the
+  // S buffer as soon as chol(S) is dead, and the two buffers swap roles -- no DRAM round trip on the item's critical
+  // path (ncu before: long-scoreboard 2.8 stalls per issue).  Needs 16-byte rows: dx % 4 == 0 and aligned bases.
+  constexpr bool BULK = LEAN && (D == 64);
+  void* mbar = reinterpret_cast<void*>(s.dg + CholWs<D>::WORDS);  // the 16 spare words behind the workspace
+  const bool bulk_ok = BULK && (a.d.dx % 4 == 0) && (a.d.Ps.time % 4 == 0) &&
+                       (reinterpret_cast<uintptr_t>(a.Ps + unit_off(a.d.Ps, 0, 0)) % 16 == 0) &&
+                       (a.d.Ps.chain % 4 == 0) && (a.d.Ps.batch % 4 == 0);
+  unsigned mphase = 0;
+  if (BULK) {
+    if (threadIdx.x == 0 && bulk_ok) mbar_init(mbar, 1);
+    __syncthreads();
+  }
   if (PAD) {  // identity on the padded diagonal of S and P: factorisations / solves run guard-free over D
     if (threadIdx.x >= a.d.dx && threadIdx.x < D) {
       s.S[threadIdx.x * LD + threadIdx.x] = T(1);
@@ -223,6 +236,18 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
     warp_stage_mat_async<T, LD>(s.S, Pg + (int64_t)t_lo * a.d.Ps.time, dx);
     if (i < dx) { m_n = mg[(int64_t)t_lo * a.d.ms.time + i]; e_n = eg[(int64_t)t_lo * a.d.eps.time + i]; }
   }
+  auto bulk_stage = [&](int tt) {  // P_tt -> the S buffer, rows by the TMA unit
+    fence_async_smem();
+    cta_sync<D>();
+    if (i == 0) mbar_expect(mbar, (unsigned)(dx * dx * sizeof(T)));
+    cta_sync<D>();
+    if (i < dx) {
+      bulk_g2s(s.S + i * LD, Pg + (int64_t)tt * a.d.Ps.time + (int64_t)i * dx, (unsigned)(dx * sizeof(T)), mbar);
+      m_n = mg[(int64_t)tt * a.d.ms.time + i];
+      e_n = eg[(int64_t)tt * a.d.eps.time + i];
+    }
+  };
+  if (BULK && bulk_ok && t_lo < t_hi) bulk_stage(t_lo);
   for (int it = 0; it < kTileLen; ++it) {
     if (W > 1) __syncthreads();  // keeps the CTA's warps on the same instruction-cache lines
     const int t = t_lo + it;
@@ -231,6 +256,12 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
     cta_sync<D>();
     if (PAD) {
       cp_async_wait_all();
+      T* sw = s.P; s.P = s.S; s.S = sw;
+      if (i < dx) { s.m[i] = m_n; s.eps[i] = e_n; }
+      cta_sync<D>();
+    } else if (BULK && bulk_ok) {
+      mbar_wait(mbar, mphase);
+      mphase ^= 1u;
       T* sw = s.P; s.P = s.S; s.S = sw;
       if (i < dx) { s.m[i] = m_n; s.eps[i] = e_n; }
       cta_sync<D>();
@@ -307,6 +338,7 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
       warp_stage_mat_async<T, LD>(s.S, Pg + (int64_t)(t + 1) * a.d.Ps.time, dx);
       if (i < dx) { m_n = mg[(int64_t)(t + 1) * a.d.ms.time + i]; e_n = eg[(int64_t)(t + 1) * a.d.eps.time + i]; }
     }
+    if (BULK && bulk_ok && t + 1 < t_hi) bulk_stage(t + 1);  // chol(S) is dead: the TMA unit refills its buffer
     chol_nan_to_zero<T, D, PAD>(s.P, s.dg, dx);             // L = chol(Sigma), NaN -> 0
     if (PAD) {
       mv_tn_pad<T, D, 2>(s.Z, s.r, s.e, s.m);               // e = m - G (F m + b)     (G v = (G^T)^T v)

@@ -116,6 +116,32 @@ template <int BYTES> __device__ __forceinline__ void cp_async(void* smem, const 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completed on an mbarrier --------------------------------------
+// One elected thread arms the barrier with the byte count (`mbar_expect`), any thread may then issue row copies of a
+// multiple of 16 bytes between 16-byte aligned addresses; consumers spin on the phase parity.  The copy engine writes
+// shared memory through the async proxy: `fence_async_smem` orders the CTA's earlier generic accesses of the
+// destination before it.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // One warp: compact global [d][d] -> padded shared [d][LD] (LD even), asynchronously.  Even d: 2 elements per copy.
 template <typename T, int LD> __device__ __forceinline__ void warp_stage_mat_async(T* dst, const T* src, int d) {
   const unsigned magic = 0xffffffffu / (unsigned)d + 1u;  // e / d exactly for e < 2^13, d <= 32

@@ -225,6 +225,15 @@ typedef struct auxssm_csmc_desc {
   uint64_t rng_seed;
   uint64_t rng_counter;
   const uint64_t* rng_counter_ptr;
+  /* Time-varying prior dynamics -- the reference scans the `Mt.params` pytree over t (csmc.py:103).  When
+   * dyn_time_varying != 0: F is [T-1,d,d], b is [T-1,d], chol_Q is [T-1,d,d]; entry t-1 is the transition INTO time
+   * step t.  BOOTSTRAP / INDEPENDENT (gradient = 0) proposals; served by the one-thread-per-particle kernel.       */
+  int32_t dyn_time_varying;
+  /* Backward sampling with Pt != Mt (csmc.py:47-50, :127-149): a linear-Gaussian Pt given by device pointers of the
+   * call's dtype, laid out like F, b, chol_Q (time-varying together with them).  All NULL: Pt is Mt.               */
+  const void* pt_F;
+  const void* pt_b;
+  const void* pt_chol_Q;
 } auxssm_csmc_desc;
 
 size_t auxssm_csmc_scratch_bytes(const auxssm_csmc_desc* desc, int32_t elem_size);
