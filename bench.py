@@ -689,6 +689,43 @@ def few_chain_leg(ctx, args):
             "value": T / (ms_graph * 1e-3), "unit": UNIT}
 
 
+def pit_leg(ctx, args):
+    """SURVEY 8(f)-3 (secondary, rank 0): parallel-in-time cSMC of csmc/independent.py:78-118 on the d = 1 SV model,
+    N = 64 particles, T = 1024, 512 chains: log2(T) + 1 = 11 stitch launches per sweep, N^2 weights per boundary."""
+    torch = ctx.torch
+    from aux_ssm_samplers_b200 import _lib, csmc
+    from aux_ssm_samplers_b200.draws import PhiloxDraws
+    d, N, T, C = 1, 64, 1024, 512
+    dtype, es = torch.float32, 4
+    (m0, P0, F, Q, b), xs_true, ys = make_data(d, T, 20250006)
+    to = lambda a: torch.as_tensor(np.asarray(a), dtype=dtype, device=ctx.device)
+    M0 = csmc.GaussianDistribution(to(m0), to(P0))
+    Mt = csmc.LinearGaussianDynamics(to(F), to(Q), to(b))
+    G = csmc.StochasticVolatilityPotential(to(ys))
+    _, kern = csmc.get_independent_kernel(M0, G, Mt, G, N, gradient=True, parallel=True)
+    rng = np.random.default_rng(20250006)
+    box = {"st": csmc.CSMCState(to(xs_true[None] + 0.3 * rng.standard_normal((C, T, d))), None)}
+    key = PhiloxDraws(20250006, ctx.device)
+
+    def step(i):
+        box["st"] = kern(key, box["st"], 0.5)
+
+    step(0)
+    n0 = _lib.launch_count()
+    ms = ctx.timed(step, 3)
+    launches = (_lib.launch_count() - n0) // 3
+    # per (time step x chain): the N^2 weights are never in HBM; particles N d s written once and gathered twice,
+    # log-weights / origins N (s + 4) read and rewritten once per level that touches the row (log2 T levels)
+    levels = int(np.ceil(np.log2(T)))
+    alg_bytes = N * d * es * 3 + levels * 2 * N * (es + 4)
+    return {"config": "extra: parallel-in-time cSMC (independent.py parallel=True), d=1 SV, N=%d, T=%d, %d chains" % (N, T, C),
+            "value": T * C / (ms * 1e-3), "unit": UNIT, "ms_per_sweep": ms, "launches_per_sweep": int(launches),
+            "stitch_weights_per_s": (T - 1) * C * N * N / (ms * 1e-3), "alg_bytes_per_unit": alg_bytes,
+            "updated_fraction": float(box["st"].updated.float().mean().item()),
+            "all_finite": bool(torch.isfinite(box["st"].x).all().item()), "dtype": "f32",
+            "draws": "generated in the kernels (Philox)"}
+
+
 def run_gpu(args):
     ctx = Ctx()
     torch = ctx.torch
@@ -712,9 +749,10 @@ def run_gpu(args):
     torch.cuda.empty_cache()
     csmc_legs = [] if args.skip_csmc else [csmc_leg(ctx, name, args, peaks) for name in CSMC_CFG]
     cfg5 = None if args.skip_cfg5 else config5_leg(ctx, args)
-    few = None
+    few = pit = None
     if ctx.rank == 0 and not args.skip_few:
         few = few_chain_leg(Ctx0(ctx), args)
+        pit = pit_leg(Ctx0(ctx), args)
     ctx.barrier()
     if ctx.rank == 0:
         d, T, C = k["d"], k["T"], k["C"]
@@ -735,7 +773,7 @@ def run_gpu(args):
             "clocks": k["clock_info"], "e2e": k["e2e"], "gpu_launches": k["launches"], "kernels": k["kernels_seen"],
             "roofline": k["roofline"], "roofline_other": k["roofline_other"], "kernel_ms": k["kernel_ms"],
             "accept_rate_last_step": k["accept_rate"], "all_finite": k["finite"], "diagnostics": diag,
-            "csmc": csmc_legs, "config5": cfg5, "few_chain": few,
+            "csmc": csmc_legs, "config5": cfg5, "few_chain": few, "pit_csmc": pit,
         }
         if ctx.world == 1 and not args.no_cpu:
             cores = len(os.sched_getaffinity(0))
