@@ -123,7 +123,7 @@ __device__ __forceinline__ void bwd_solve(const T* L, T* B, const T* dg, int n, 
 // as 2-element vectors.
 // S_ab = f_a f_b P_ab + Q_ab,  Z_ab = f_a P_ab  (time-invariant diagonal F; fd is zero beyond dx)
 template <typename T, int D>
-__device__ __forceinline__ void lean_predict_rows(const T* P, const T* fd, const T* __restrict__ Qg, T* S, T* Z, int dx) {
+__device__ __forceinline__ void lean_predict_rows(const T* P, const T* fd, const T* Qs, T* S, T* Z, int dx) {
   constexpr int LD = Tile<D>::LD, LPR = D / 4, RPP = 32 / LPR;
   const int lane = threadIdx.x & 31, lr = lane / LPR, c4 = (lane % LPR) * 4;
   T fc[4];
@@ -132,13 +132,12 @@ __device__ __forceinline__ void lean_predict_rows(const T* P, const T* fd, const
   for (int r0 = 0; r0 < dx; r0 += RPP) {
     const int r = r0 + lr;
     if (r < dx) {
-      T pv[4], qa[2] = {T(0), T(0)}, qb[2] = {T(0), T(0)}, s4[4], z4[4];
+      T pv[4], q4[4], s4[4], z4[4];
       ldv<T, 4>(pv, P + r * LD + c4);
-      if (c4 < dx) ldv<T, 2>(qa, Qg + r * dx + c4);
-      if (c4 + 2 < dx) ldv<T, 2>(qb, Qg + r * dx + c4 + 2);
+      ldv<T, 4>(q4, Qs + r * LD + c4);  // the CTA's shared, zero-padded image of the time-invariant Q
       const T fa = fd[r];
-      s4[0] = fma_(fa * fc[0], pv[0], qa[0]); s4[1] = fma_(fa * fc[1], pv[1], qa[1]);
-      s4[2] = fma_(fa * fc[2], pv[2], qb[0]); s4[3] = fma_(fa * fc[3], pv[3], qb[1]);
+      s4[0] = fma_(fa * fc[0], pv[0], q4[0]); s4[1] = fma_(fa * fc[1], pv[1], q4[1]);
+      s4[2] = fma_(fa * fc[2], pv[2], q4[2]); s4[3] = fma_(fa * fc[3], pv[3], q4[3]);
 #pragma unroll
       for (int q = 0; q < 4; ++q) z4[q] = fa * pv[q];
       stv<T, 4>(S + r * LD + c4, s4);
@@ -170,6 +169,8 @@ template <typename T, int D> __device__ __forceinline__ void store_rows_pairs(T*
 template <typename T, int D, bool LEAN> struct ElemCfg {
   static constexpr int W = (LEAN && D <= 32) ? 7 : 1;  // (four D = 64 items per CTA were measured: no gain)
   static constexpr int MINB = (Occ<T, D>::MINB / W) > 0 ? Occ<T, D>::MINB / W : 1;
+  // (a 144-register cap through __maxnreg__ was measured: 15.3 ms per call instead of 11.4 -- ptxas spills the same
+  // loop-invariant addresses either way and schedules worse; the 128 registers of __launch_bounds__(224, 2) stay)
 };
 
 // pass 1: (G_t^T, e_t) for one unit and a tile of time steps
@@ -190,6 +191,19 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
   T* fd = p; p += D;  // diag(F) (LEAN)
   s.dg = p;
   constexpr bool PAD = LEAN && (D <= 32);
+  // PAD path: one zero-padded image of the time-invariant Q per CTA, shared by its W work items (behind their private
+  // regions).  Reading Q_ab from global memory for every item was the kernel's long-scoreboard stall (1.35 per issue).
+  T* sQ = reinterpret_cast<T*>(smem_raw) + (size_t)W * samp_smem_elems<D>(LEAN);
+  const bool q_shared = PAD && a.d.Qs.chain == 0 && a.d.Qs.batch == 0 && a.Qs != nullptr;
+  if (q_shared) {
+    const T* Qg0 = a.Qs + unit_off(a.d.Qs, 0, 0);  // chain- and batch-shared (checked by the launcher)
+    const int tid = threadIdx.y * NT + threadIdx.x, nthr = NT * W;
+    for (int e = tid; e < D * LD; e += nthr) {
+      const int r = e / LD, cc = e - r * LD;
+      sQ[e] = (r < a.d.dx && cc < a.d.dx) ? Qg0[r * a.d.dx + cc] : T(0);
+    }
+    __syncthreads();
+  }
   // D = 64: P_{t+1} is staged by the TMA unit (one cp.async.bulk per 256-byte row, completed on an mbarrier) into the
   // S buffer as soon as chol(S) is dead, and the two buffers swap roles -- no DRAM round trip on the item's critical
   // path (ncu before: long-scoreboard 2.8 stalls per issue).  Needs 16-byte rows: dx % 4 == 0 and aligned bases.
@@ -232,9 +246,33 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
   const bool pairs_ok = PAD && (dx & 1) == 0 && a.Qs != nullptr &&
                         (reinterpret_cast<uintptr_t>(a.Qs + unit_off(a.d.Qs, c, b)) % (2 * sizeof(T))) == 0 &&
                         (reinterpret_cast<uintptr_t>(a.steps) % (2 * sizeof(T))) == 0;
-  if (PAD && t_lo < t_hi) {
-    warp_stage_mat_async<T, LD>(s.S, Pg + (int64_t)t_lo * a.d.Ps.time, dx);
-    if (i < dx) { m_n = mg[(int64_t)t_lo * a.d.ms.time + i]; e_n = eg[(int64_t)t_lo * a.d.eps.time + i]; }
+  // PAD path: the four advancing global pointers of an item (next P_t / m_t / eps_t to prefetch, current output slot)
+  // live in the item's spare shared words, not in registers: they are touched twice per item, and keeping them (plus
+  // the indices they derive from) live across the factorisations made ptxas spill to local memory, whose reloads
+  // missed the small L1 the streaming P tiles leave over (ncu: 8 % of the kernel in long-scoreboard stalls on LDL).
+  volatile unsigned long long* ctx = reinterpret_cast<volatile unsigned long long*>(s.dg + CholWs<D>::WORDS);
+  auto pad_prefetch = [&]() {
+    const T* Pn = reinterpret_cast<const T*>(ctx[0]);
+    const T* mn = reinterpret_cast<const T*>(ctx[1]);
+    const T* en = reinterpret_cast<const T*>(ctx[2]);
+    warp_stage_mat_async<T, LD>(s.S, Pn, dx);
+    if (i < dx) { m_n = mn[i]; e_n = en[i]; }
+    __syncwarp();
+    if (i == 0) {
+      ctx[0] = reinterpret_cast<unsigned long long>(Pn + a.d.Ps.time);
+      ctx[1] = reinterpret_cast<unsigned long long>(mn + a.d.ms.time);
+      ctx[2] = reinterpret_cast<unsigned long long>(en + a.d.eps.time);
+    }
+  };
+  if (PAD) {
+    if (i == 0) {
+      ctx[0] = reinterpret_cast<unsigned long long>(Pg + (int64_t)t_lo * a.d.Ps.time);
+      ctx[1] = reinterpret_cast<unsigned long long>(mg + (int64_t)t_lo * a.d.ms.time);
+      ctx[2] = reinterpret_cast<unsigned long long>(eg + (int64_t)t_lo * a.d.eps.time);
+      ctx[3] = reinterpret_cast<unsigned long long>(a.steps + ((int64_t)ul * Tn + t_lo) * ssz);
+    }
+    __syncwarp();
+    if (t_lo < t_hi) pad_prefetch();
   }
   auto bulk_stage = [&](int tt) {  // P_tt -> the S buffer, rows by the TMA unit
     fence_async_smem();
@@ -252,7 +290,7 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
     if (W > 1) __syncthreads();  // keeps the CTA's warps on the same instruction-cache lines
     const int t = t_lo + it;
     if (t >= t_hi) { if (W > 1) continue; else break; }
-    T* g = a.steps + ((int64_t)ul * Tn + t) * ssz;
+    T* g = PAD ? nullptr : a.steps + ((int64_t)ul * Tn + t) * ssz;
     cta_sync<D>();
     if (PAD) {
       cp_async_wait_all();
@@ -276,21 +314,22 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
       // last step: x_{T-1} = m + chol(P) eps  (sampling.py:116-124)
       chol_nan_to_zero<T, D, PAD>(s.P, s.dg, dx);
       if (PAD) mv_nn_pad<T, D, 1>(s.P, s.eps, s.e, s.m); else mv_nn<T, D, 1>(s.P, s.eps, s.e, s.m, dx, dx);
+      if (PAD) g = reinterpret_cast<T*>(ctx[3]);
       if (i < dx) g[dx * dx + i] = s.e[i];
       continue;
     }
     if (LEAN) {
       // time-invariant diagonal F: S_ab = f_a f_b P_ab + Q_ab, (F P)_ab = f_a P_ab, r = f m + b   (O(d^2))
-      const T* Fg = a.Fs + unit_off(a.d.Fs, c, b);
-      const T* Qg = a.Qs + unit_off(a.d.Qs, c, b);
       if (first_dyn) {
+        const T* Fg = a.Fs + unit_off(a.d.Fs, c, b);
         if (i < dx) { fd[i] = Fg[i * dx + i]; s.bv[i] = a.bs[unit_off(a.d.bs, c, b) + i]; }
         first_dyn = false;
       }
       cta_sync<D>();
-      if (PAD && pairs_ok) {
-        lean_predict_rows<T, D>(s.P, fd, Qg, s.S, s.Z, dx);
+      if (PAD && q_shared) {
+        lean_predict_rows<T, D>(s.P, fd, sQ, s.S, s.Z, dx);
       } else {
+        const T* Qg = a.Qs + unit_off(a.d.Qs, c, b);
         AUXSSM_FOR_ROWS(ri, rj, dx, dx) {
           const T fa = fd[ri], pv = s.P[ri * LD + rj];
           s.S[ri * LD + rj] = fma_(fa * fd[rj], pv, Qg[ri * dx + rj]);
@@ -334,10 +373,7 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
     fwd_solve<T, D, PAD>(s.S, s.Z, nullptr, dx, dx, s.dg);  // Zs = Ls^{-1} F P
     mm_tn<T, D, 2>(s.Z, s.Z, s.P, s.P, PAD ? D : dx);       // Sigma = P - Zs^T Zs  (lower triangle feeds the Cholesky)
     bwd_solve<T, D, PAD>(s.S, s.Z, s.dg, dx, dx);           // Z <- G^T = Ls^{-T} Zs
-    if (PAD && t + 1 < t_hi) {                              // chol(S) is dead: its buffer receives P_{t+1}
-      warp_stage_mat_async<T, LD>(s.S, Pg + (int64_t)(t + 1) * a.d.Ps.time, dx);
-      if (i < dx) { m_n = mg[(int64_t)(t + 1) * a.d.ms.time + i]; e_n = eg[(int64_t)(t + 1) * a.d.eps.time + i]; }
-    }
+    if (PAD && t + 1 < t_hi) pad_prefetch();                // chol(S) is dead: its buffer receives P_{t+1}
     if (BULK && bulk_ok && t + 1 < t_hi) bulk_stage(t + 1);  // chol(S) is dead: the TMA unit refills its buffer
     chol_nan_to_zero<T, D, PAD>(s.P, s.dg, dx);             // L = chol(Sigma), NaN -> 0
     if (PAD) {
@@ -347,8 +383,13 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
       mv_tn<T, D, 2>(s.Z, s.r, s.e, s.m, dx, dx);
       mv_nn<T, D, 1>(s.P, s.eps, s.e, s.e, dx, dx);
     }
+    if (PAD) g = reinterpret_cast<T*>(ctx[3]);
     if (PAD && pairs_ok) store_rows_pairs<T, D>(g, s.Z, dx); else store_mat<T, D>(g, s.Z, dx, dx);
     if (i < dx) g[dx * dx + i] = s.e[i];
+    if (PAD) {
+      __syncwarp();
+      if (i == 0) ctx[3] = reinterpret_cast<unsigned long long>(g + ssz);
+    }
   }
 }
 
@@ -447,7 +488,8 @@ template <typename T, int D> static int launch_sample(cudaStream_t st, SampleArg
     if (rc) return rc;
   }
   constexpr int WL = ElemCfg<T, D, true>::W, WG = ElemCfg<T, D, false>::W;
-  const size_t smem_l = samp_smem_elems<D>(true) * sizeof(T) * WL, smem_g = samp_smem_elems<D>(false) * sizeof(T) * WG;
+  const size_t smem_l = samp_smem_elems<D>(true) * sizeof(T) * WL + (D <= 32 ? (size_t)D * Tile<D>::LD * sizeof(T) : 0);
+  const size_t smem_g = samp_smem_elems<D>(false) * sizeof(T) * WG;
   if (lean) rc = ensure_smem(sample_elements_kernel<T, D, true>, smem_l, "auxssm_kalman_sample");
   if (rc) return rc;
   // The general kernel does not fit the shared memory of one CTA at d = 64 in fp64.  Without the hint that is an
