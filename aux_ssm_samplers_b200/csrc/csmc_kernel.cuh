@@ -20,6 +20,14 @@
 
 namespace auxssm {
 
+// The backward pass consumes ONE uniform per time step, the same for every thread of the CTA.  A Philox block holds
+// 4 (fp32) / 2 (fp64) consecutive elements, so each thread keeps the last block it generated instead of running the
+// generator once per step (a quarter / half of the backward pass's generator work).
+template <typename T> struct BwdCache {
+  uint64_t blk = ~(uint64_t)0;
+  T v[PhiloxPer<T>::N];
+};
+
 template <typename T> struct CsmcArgs {
   auxssm_csmc_desc d;
   const T *x_star, *m0, *Lp0, *F, *b, *Lq, *ys, *u, *shd, *grad, *K, *cL, *normals, *u_res, *u_kill, *u_bwd;
@@ -43,6 +51,13 @@ template <typename T> struct CsmcArgs {
   }
   __device__ __forceinline__ T draw_u_bwd(int64_t e) const {
     return rng.on ? philox_elem<T>(PHILOX_UNIFORM, rng.seed, call_bwd(), (uint64_t)e) : u_bwd[e];
+  }
+  __device__ __forceinline__ T draw_u_bwd(int64_t e, BwdCache<T>& bc) const {
+    if (!rng.on) return u_bwd[e];
+    constexpr int PER = PhiloxPer<T>::N;
+    const uint64_t blk = (uint64_t)e / PER;
+    if (blk != bc.blk) { philox_block(PHILOX_UNIFORM, rng.seed, call_bwd(), blk, bc.v); bc.blk = blk; }
+    return philox_pick(bc.v, (int)((uint64_t)e % PER));
   }
   template <int NMAX> __device__ __forceinline__ void draw_normals(int64_t e0, int n, T (&out)[NMAX]) const {
     if (rng.on) {
@@ -556,9 +571,10 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
     T* xo = a.x_out + (int64_t)c * Tn * d;
     int32_t* ao = a.anc + (int64_t)c * Tn;
     const int64_t ub = (int64_t)c * Tn;
+    BwdCache<T> bwdc;
     // B_T ~ Cat(w_T): index = #{j : cdf[j] < r}, clamped (csmc.py:111 / :131)
     {
-      const T r = cdf[N - 1] * (T(1) - a.draw_u_bwd(ub));
+      const T r = cdf[N - 1] * (T(1) - a.draw_u_bwd(ub, bwdc));
       int B = __syncthreads_count(active && cdf[i] < r);
       if (B > N - 1) B = N - 1;
       if (i == B) {
@@ -573,13 +589,13 @@ __global__ void __launch_bounds__(MAXT) csmc_sweep_kernel(CsmcArgs<T> a) {
       __syncthreads();
     }
     if (dsc.backward) {
-      T ub_n = (Tn > 1) ? a.draw_u_bwd(ub + 1) : T(0);
+      T ub_n = (Tn > 1) ? a.draw_u_bwd(ub + 1, bwdc) : T(0);
       if (pt_differs && !tv && Tn > 1) load_dynamics(ptF, ptb, ptLq, 0);
       for (int t = Tn - 2, k2 = 1; t >= 0; --t, ++k2) {
         T xt[D], xpred[D], xsel[D];
         T lwh = T(0);
         const T ub_c = ub_n;
-        if (t > 0) ub_n = a.draw_u_bwd(ub + k2 + 1);
+        if (t > 0) ub_n = a.draw_u_bwd(ub + k2 + 1, bwdc);
         if (tv && (pt_differs || t < Tn - 2)) load_dynamics(ptF, ptb, ptLq, t);  // Pt(x_{t+1} | x_t): entry t
         {
           // history of step t, staged with coalesced loads

@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(256, (D == 1 && sizeof(T) == 4) ? 4 : 1) csmc_
     T* xo = a.x_out + (int64_t)c * Tn * d;
     int32_t* ao = a.anc + (int64_t)c * Tn;
     const int64_t ub = (int64_t)c * Tn;
+    BwdCache<T> bwdc;
     // B = min(#{j : cdf[j] < r}, N - 1) (csmc.py:111 / :131): per-thread counts, warp add, one shared atomic per
     // warp; the owner of particle B then publishes it as the selected state.  All threads call (three barriers).
     auto select = [&](T r, const T (&xc)[PPT][D], int t) {
@@ -319,11 +320,11 @@ __global__ void __launch_bounds__(256, (D == 1 && sizeof(T) == 4) ? 4 : 1) csmc_
     {
       if (i == 0) isel[0] = 0;
       __syncthreads();
-      const T r = cdf[N - 1] * (T(1) - a.draw_u_bwd(ub));
+      const T r = cdf[N - 1] * (T(1) - a.draw_u_bwd(ub, bwdc));
       B_last = select(r, xn, Tn - 1);
     }
     if (dsc.backward) {
-      T ub_n = (Tn > 1) ? a.draw_u_bwd(ub + 1) : T(0);
+      T ub_n = (Tn > 1) ? a.draw_u_bwd(ub + 1, bwdc) : T(0);
       T xt_n[PPT][D], lwh_n[PPT];
 #pragma unroll
       for (int q = 0; q < PPT; ++q) {
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(256, (D == 1 && sizeof(T) == 4) ? 4 : 1) csmc_
           for (int k = 0; k < D; ++k) xt[q][k] = xt_n[q][k];
         }
         const T ub_c = ub_n;
-        if (t > 0) ub_n = a.draw_u_bwd(ub + k2 + 1);
+        if (t > 0) ub_n = a.draw_u_bwd(ub + k2 + 1, bwdc);
         fetch(t - 1);
         T xsel[D];
 #pragma unroll

@@ -559,10 +559,11 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
     T* xo = a.x_out + (int64_t)c * Tn * d;
     int32_t* ao = a.anc + (int64_t)c * Tn;
     const int64_t ub = (int64_t)c * Tn;
+    BwdCache<T> bwdc;
     T* cur = other;  // staging buffers of the backward pass: the two particle buffers, `part` read first
     T* nxt = part;
     {
-      const T r = cdf[N - 1] * (T(1) - a.draw_u_bwd(ub));
+      const T r = cdf[N - 1] * (T(1) - a.draw_u_bwd(ub, bwdc));
       int B = __syncthreads_count(active && cdf[i] < r);
       if (B > N - 1) B = N - 1;
       if (i < D) {
@@ -575,12 +576,12 @@ __global__ void __launch_bounds__(256, 1) csmc_wide_kernel(CsmcArgs<T> a) {
     }
     if (dsc.backward) {
       if (Tn > 1) stage_rows_async<T, LD>(cur, xs_h + (int64_t)(Tn - 2) * N * d, N * d, d, magic);
-      T ub_n = (Tn > 1) ? a.draw_u_bwd(ub + 1) : T(0);
+      T ub_n = (Tn > 1) ? a.draw_u_bwd(ub + 1, bwdc) : T(0);
       T lwh_n = (Tn > 1 && active) ? lw_h[(int64_t)(Tn - 2) * N + i] : T(0);
       for (int t = Tn - 2, k2 = 1; t >= 0; --t, ++k2) {
         const T ub_c = ub_n, lwh = lwh_n;
         if (t > 0) {
-          ub_n = a.draw_u_bwd(ub + k2 + 1);
+          ub_n = a.draw_u_bwd(ub + k2 + 1, bwdc);
           if (active) lwh_n = lw_h[(int64_t)(t - 1) * N + i];
         }
         cp_async_wait_all();
