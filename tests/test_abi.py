@@ -63,3 +63,14 @@ def test_reference_api_surface():
     st = init(torch.zeros(3, 2))
     assert st.updated is True and st.x.shape == (3, 2)
     assert pkg.LGSSM._fields == ("m0", "P0", "Fs", "Qs", "bs", "Hs", "Rs", "cs")
+
+
+def test_package_import_is_lazy_and_the_abi_module_is_torch_free():
+    """`import aux_ssm_samplers_b200._abi` / `.raw` must not import torch (checked in a child process)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.modules['torch'] = None; sys.path.insert(0, %r); "
+            "import aux_ssm_samplers_b200, aux_ssm_samplers_b200._abi as a, aux_ssm_samplers_b200.raw; "
+            "print(len(a.exported_symbols()))" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and int(r.stdout.strip()) >= 60, r.stderr[-2000:]
