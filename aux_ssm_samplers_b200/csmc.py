@@ -13,12 +13,16 @@ Same names and argument meaning as the reference:
 * unfused primitives ``normalize``, ``multinomial``, ``killing``, ``categorical``
   (math/utils.py:24-39, resamplings.py:14-37, csmc.py:111)
 
-The reference calls user Python callables inside its time loop.  A fused CUDA sweep cannot, so the
-model pieces are *descriptors* from a closed family set (see include/auxssm.h): a linear-Gaussian
-prior (``GaussianDistribution`` + ``LinearGaussianDynamics``) with a ``Flat`` / ``GaussianObservation`` /
-``StochasticVolatility`` potential, proposed from the prior (bootstrap), from the independent auxiliary
-proposal, or from the guided auxiliary proposal.  Anything else raises ``NotImplementedError`` and
-must be written against the unfused primitives.
+The reference calls user Python callables inside its time loop.  A fused CUDA sweep cannot, so there are two paths:
+
+* *descriptors* from a closed family set (see include/auxssm.h) -- a linear-Gaussian prior (``GaussianDistribution`` +
+  ``LinearGaussianDynamics``, time-invariant or time-varying) with a ``Flat`` / ``GaussianObservation`` /
+  ``StochasticVolatility`` potential, proposed from the prior (bootstrap), from the independent auxiliary proposal, or
+  from the guided auxiliary proposal -- run the whole sweep in ONE persistent kernel;
+* any other model given as objects with the reference's callable interface (``M0.sample(key, N)``, ``G0(x)``,
+  ``Mt.sample(key, x, params_t)``, ``Gt(x_t, x_prev, params_t)``, ``Pt.logpdf``; csmc/base.py:24-71) runs through
+  ``_get_callable_kernel``: the time loop stays on the host like ``lax.scan``, the user's callables are evaluated once
+  per step, and normalisation / conditional resampling / categorical draws use the unfused kernels.
 
 ``state.x`` is ``[C, T, d]`` (chains leading) or ``[T, d]``.  ``key`` is a draws object (``draws.py``);
 call order: normals ``[C,T,d]`` (auxiliary kernels only), normals ``[C,T,N,d]``, uniforms ``[C,T-1,N]``,
@@ -248,6 +252,8 @@ def get_kernel(M0, G0, Mt, Gt, N, backward=False, Pt=None, *, resampling="multin
         Pt = Mt
     elif backward and not hasattr(Pt, "logpdf"):
         raise ValueError("When `backward` is True, `Pt` must implement a valid logpdf method.")
+    if _aux is None and _is_user_model(M0, G0, Mt, Gt):
+        return _get_callable_kernel(M0, G0, Mt, Gt, N, backward, Pt, resampling)
     pot = _check_family(M0, G0, Mt, Gt)
     if backward and Pt is not Mt and not isinstance(Pt, LinearGaussianDynamics):
         raise NotImplementedError("backward sampling needs a LinearGaussianDynamics `Pt` (closed family set)")
@@ -259,6 +265,96 @@ def get_kernel(M0, G0, Mt, Gt, N, backward=False, Pt=None, *, resampling="multin
         T = x_star.shape[-2]
         shape = x_star.shape[:-2] + (T,)
         return CSMCState(x=x_star, updated=torch.ones(shape, dtype=torch.bool, device=x_star.device))
+
+    return init, kernel
+
+
+# ---- user-defined models: the reference's callables, one time step at a time --------------------------------------
+
+def _is_user_model(M0, G0, Mt, Gt):
+    """True when the four pieces are user objects with the reference's callable interface (csmc/base.py:24-71)
+    rather than descriptors of the closed family set."""
+    closed = isinstance(M0, GaussianDistribution) or isinstance(Mt, LinearGaussianDynamics) or hasattr(G0, "kind") \
+        or hasattr(Gt, "kind")
+    return (not closed) and callable(getattr(M0, "sample", None)) and callable(G0) and \
+        callable(getattr(Mt, "sample", None)) and callable(Gt)
+
+
+def _params_at(params, k):
+    """Entry k of a parameter pytree whose leaves have a leading time axis (what ``lax.scan`` does with
+    ``Mt.params`` / ``Gt.params``, csmc.py:103)."""
+    if params is None:
+        return None
+    if isinstance(params, (tuple, list)):
+        return type(params)(_params_at(p, k) for p in params)
+    if isinstance(params, dict):
+        return {n: _params_at(p, k) for n, p in params.items()}
+    return params[k]
+
+
+def _get_callable_kernel(M0, G0, Mt, Gt, N, backward, Pt, resampling):
+    """``get_kernel`` of csmc.py:16-66 for ARBITRARY user models: ``M0.sample(key, N)``, ``G0(x)``,
+    ``Mt.sample(key, x_prev, params_t)``, ``Gt(x_t, x_prev, params_t)`` and ``Pt.logpdf(x_next, xs_t, params_t)`` are the
+    user's own (torch) callables, exactly the reference's signatures; they are called once per time step from the host,
+    like ``lax.scan`` calls them (csmc.py:82-103, :134-146), and everything between them -- ``normalize``
+    (math/utils.py:24-39), conditional resampling (resamplings.py:14-86), the categorical draws of the backward pass
+    (csmc.py:111,131,138) -- runs in the library's unfused kernels.  Slower than the fused sweeps (2-4 launches per time
+    step), but any model works.  Callables see tensors with a leading chain axis when ``state.x`` is ``[C, T, d]``
+    (``M0.sample(key, N) -> [C, N, d]`` etc.) and none when it is ``[T, d]``; ``key`` is the draws object (``draws.py``).
+    Draw order: per step the callables' own draws, then ``uniform((.., N))`` (or ``(.., 3)`` systematic; killing draws
+    the kill uniforms first), and in the backward pass one ``uniform((..,))`` per step starting with B_T."""
+    def resample(key, w):
+        shape = w.shape
+        if resampling == "multinomial":
+            return multinomial(key.uniform(shape, w.dtype, w.device), w)
+        if resampling == "killing":
+            uk = key.uniform(shape, w.dtype, w.device)
+            return killing(uk, key.uniform(shape, w.dtype, w.device), w)
+        if resampling == "systematic":
+            return systematic(key.uniform(shape[:-1] + (3,), w.dtype, w.device), w)
+        raise ValueError(resampling)
+
+    def take(x, idx):  # x [.., N, d], idx [.., K] -> [.., K, d]
+        return torch.gather(x, -2, idx.long().unsqueeze(-1).expand(idx.shape + (x.shape[-1],)))
+
+    def kernel(key, state):
+        x_star = state.x
+        T = x_star.shape[-2]
+        batch = x_star.shape[:-2]
+        xs, lws, As = [], [], []
+        x = M0.sample(key, N)
+        _lib.require_cuda(x_star, x)
+        x = x.clone()
+        x[..., 0, :] = x_star[..., 0, :]                       # csmc.py:76
+        lw = G0(x)
+        w = normalize(lw)
+        xs.append(x); lws.append(lw)
+        for t in range(1, T):
+            A = resample(key, w)
+            xp = take(x, A)
+            x = Mt.sample(key, xp, _params_at(getattr(Mt, "params", None), t - 1)).clone()
+            x[..., 0, :] = x_star[..., t, :]                   # :92
+            lw = Gt(x, xp, _params_at(getattr(Gt, "params", None), t - 1))
+            w = normalize(lw)
+            xs.append(x); lws.append(lw); As.append(A)
+        B = categorical(key.uniform(batch, w.dtype, w.device), w)
+        out_x, out_B = [None] * T, [None] * T
+        out_B[T - 1] = B
+        out_x[T - 1] = take(xs[T - 1], B.unsqueeze(-1)).squeeze(-2)
+        for t in range(T - 2, -1, -1):
+            if backward:                                       # csmc.py:134-146
+                lwb = Pt.logpdf(out_x[t + 1].unsqueeze(-2), xs[t], _params_at(getattr(Pt, "params", None), t)) + lws[t]
+                B = categorical(key.uniform(batch, w.dtype, w.device), normalize(lwb))
+            else:                                              # :116-121
+                B = torch.gather(As[t], -1, B.long().unsqueeze(-1)).squeeze(-1)
+            out_B[t] = B
+            out_x[t] = take(xs[t], B.unsqueeze(-1)).squeeze(-2)
+        anc = torch.stack(out_B, dim=-1)
+        return CSMCState(x=torch.stack(out_x, dim=-2), updated=anc != 0)
+
+    def init(x_star):
+        T = x_star.shape[-2]
+        return CSMCState(x=x_star, updated=torch.ones(x_star.shape[:-2] + (T,), dtype=torch.bool, device=x_star.device))
 
     return init, kernel
 
@@ -281,7 +377,9 @@ def get_generic_kernel(factory, N, backward=False, Pt=None, *, resampling="multi
     """Auxiliary particle Gibbs with generic proposals (csmc/generic.py:14-79).
 
     ``factory(u [C,T,d], sqrt_half_delta [C,T]) -> AuxiliaryFeynmanKac`` (see ``independent_factory`` and
-    ``stochastic_volatility.guided_factory``).  ``kernel(key, state, delta)``; ``delta`` scalar, ``[T]`` or ``[C,T]``.
+    ``stochastic_volatility.guided_factory``), or four user callables ``(M0, G0, Mt, Gt)`` with the reference's
+    interface, which run on the per-step path (``_get_callable_kernel``).  ``kernel(key, state, delta)``; ``delta``
+    scalar, ``[T]`` or ``[C,T]``.
     """
     if backward and Pt is None:
         raise ValueError("If backward is True, the true dynamics `Pt` must be provided.")
@@ -295,7 +393,14 @@ def get_generic_kernel(factory, N, backward=False, Pt=None, *, resampling="multi
         u, shd = _aux_u(key, xb, delta)
         fk = factory(u, shd)
         if not isinstance(fk, AuxiliaryFeynmanKac):
-            raise NotImplementedError("factory must return an AuxiliaryFeynmanKac from the closed family set")
+            # csmc/generic.py:69-72 with the user's own callables: the per-step path on the unfused kernels.  A user
+            # factory sees exactly what the reference hands it: u [T, d], scale [T] when the state is one chain.
+            m0, g0, mt, gt = factory(u[0], shd[0]) if squeeze else fk
+            if not _is_user_model(m0, g0, mt, gt):
+                raise NotImplementedError("factory must return an AuxiliaryFeynmanKac (closed family set) or four user "
+                                          "callables with the reference's interface (csmc/base.py:24-71)")
+            _, inner = _get_callable_kernel(m0, g0, mt, gt, N, backward, Pt, resampling)
+            return inner(key, CSMCState(x, state.updated))
         _, inner = get_kernel(fk.M0, fk.G0, fk.Mt, fk.Gt, N, backward, Pt, resampling=resampling, _aux=fk.aux,
                               return_history=return_history)
         out = inner(key, CSMCState(xb, state.updated))
