@@ -679,7 +679,7 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
             for (int j = 0; j < k; ++j) piv = fma_(-L[k][j], L[k][j], piv);
             if (lane == 0) svbuf[i0 + k] = piv;   // conditional innovation variance of observation i0 + k
             T lkk;
-            pivot_<T>(piv, lkk, inv[k]);
+            pivot_fast_<T>(piv, lkk, inv[k]);
             L[k][k] = lkk;
 #pragma unroll
             for (int r = k + 1; r < NB; ++r) {

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128, 2) filter_tile_kernel(FilterArgs<T> a, in
           for (int jj = 0; jj < k; ++jj) piv = fma_(-L[k][jj], L[k][jj], piv);
           if (tid == 0) svbuf[i0 + k] = piv;
           T lkk;
-          pivot_<T>(piv, lkk, inv[k]);
+          pivot_fast_<T>(piv, lkk, inv[k]);
           L[k][k] = lkk;
 #pragma unroll
           for (int r = k + 1; r < NB; ++r) {

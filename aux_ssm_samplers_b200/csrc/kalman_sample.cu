@@ -369,7 +369,7 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
         mv_tn<T, D, 1>(s.Ft, s.m, s.r, s.bv, dx, dx);  // r = F m + b
       }
     }
-    chol_inplace<T, D, PAD>(s.S, s.dg, dx);
+    chol_inplace<T, D, PAD, PAD>(s.S, s.dg, dx);            // (PAD: the substitutions read the lower triangle only)
     fwd_solve<T, D, PAD>(s.S, s.Z, nullptr, dx, dx, s.dg);  // Zs = Ls^{-1} F P
     mm_tn<T, D, 2>(s.Z, s.Z, s.P, s.P, PAD ? D : dx);       // Sigma = P - Zs^T Zs  (lower triangle feeds the Cholesky)
     bwd_solve<T, D, PAD>(s.S, s.Z, s.dg, dx, dx);           // Z <- G^T = Ls^{-T} Zs

@@ -381,6 +381,17 @@ template <> __device__ __forceinline__ void pivot_<double>(double x, double& l, 
   l = sqrt(x);
   inv = 1.0 / l;
 }
+// The structured fp32 hot paths (one-warp sampler items, warp / tile filters) use the bare MUFU.RSQ: its documented
+// maximum relative error, 2^-22.9 = 1.3e-7, is one fp32 rounding, and the Newton step + zero guard above were 5 of the
+// ~17 non-FMA instructions on the serial path of every pivot (64 pivots per sampler item, 32 per filter step).  A zero
+// pivot gives l = 0 * inf = NaN, which the callers already treat as a failed factorisation (NaN -> 0, sampling.py:102).
+template <typename T> __device__ __forceinline__ void pivot_fast_(T x, T& l, T& inv) { pivot_<T>(x, l, inv); }
+template <> __device__ __forceinline__ void pivot_fast_<float>(float x, float& l, float& inv) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  inv = r;
+  l = x * r;
+}
 
 // Register-resident Cholesky for D <= 32: warp 0 only, lane i owns row i in registers; the freshly
 // scaled column k is exchanged through a double-buffered shared vector (one STS + (D-k)/4 broadcast
@@ -388,7 +399,9 @@ template <> __device__ __forceinline__ void pivot_<double>(double x, double& l, 
 // `colbuf` needs 2*D words.  All D x D loops are fully unrolled so the row stays in registers.
 // PADDED = the caller keeps an identity block on the padded diagonal (rows/cols >= n), so all D columns
 // can be processed without any run-time guard (branch-free, ~20% fewer instructions at d = 30).
-template <typename T, int D, bool PADDED = false>
+// KEEP_UPPER: leave whatever the elimination left above the diagonal instead of zeroing it on the way out (32 selects
+// + predicate packing per lane); for callers that only ever read the lower triangle (the substitutions).
+template <typename T, int D, bool PADDED = false, bool KEEP_UPPER = false>
 __device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n) {
   constexpr int LD = Tile<D>::LD;
   constexpr int V = (D >= 4) ? 4 : D;
@@ -408,12 +421,13 @@ __device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n
       if (PADDED || k < n) {
         const T akk = __shfl_sync(0xffffffffu, row[k], k);
         T lkk, inv;
-        pivot_<T>(akk, lkk, inv);
-        const T lik = (lane == k) ? lkk : row[k] * inv;
+        if constexpr (PADDED) pivot_fast_<T>(akk, lkk, inv); else pivot_<T>(akk, lkk, inv);
+        // PADDED (fast pivot): l_kk = a_kk * inv is what row[k] * inv gives on lane k itself, no select needed
+        const T lik = PADDED ? row[k] * inv : ((lane == k) ? lkk : row[k] * inv);
         row[k] = lik;
         T* cb = colbuf + (k & 1) * D;
         if (lane < D) cb[lane] = lik;
-        if (lane == k) {
+        if (PADDED ? (lane == 0) : (lane == k)) {  // every lane holds the same pivot: PADDED lets lane 0 publish it
           dg[k] = lkk;
           if (dginv) dginv[k] = inv;
         }
@@ -441,7 +455,7 @@ __device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n
       for (int j = 0; j < D; j += V) {
         T tmp[V];
 #pragma unroll
-        for (int q = 0; q < V; ++q) tmp[q] = (j + q <= lane) ? row[j + q] : T(0);
+        for (int q = 0; q < V; ++q) tmp[q] = (KEEP_UPPER || j + q <= lane) ? row[j + q] : T(0);
         stv<T, V>(A + lane * LD + j, tmp);
       }
     }
@@ -715,8 +729,9 @@ __device__ __forceinline__ void chol_reg64(T* A, T* dg, T* dginv, T* colbuf, int
 }
 
 // In-place lower Cholesky of the n x n block; strict upper triangle zeroed; non-PD pivots give NaN.
-template <typename T, int D, bool PADDED = false> __device__ __forceinline__ void chol_inplace(T* A, T* dg, int n) {
-  if constexpr (D <= 32) chol_reg<T, D, PADDED>(A, dg, dg + D, dg + 2 * D, n);
+template <typename T, int D, bool PADDED = false, bool KEEP_UPPER = false>
+__device__ __forceinline__ void chol_inplace(T* A, T* dg, int n) {
+  if constexpr (D <= 32) chol_reg<T, D, PADDED, KEEP_UPPER>(A, dg, dg + D, dg + 2 * D, n);
   else if constexpr (D == 64 && Tile<D>::NT >= 32) chol_reg64<T, PADDED>(A, dg, dg + D, dg + 2 * D, n);
   else chol_generic<T, D>(A, dg, n);
 }
