@@ -401,8 +401,12 @@ template <> __device__ __forceinline__ void pivot_fast_<float>(float x, float& l
 // can be processed without any run-time guard (branch-free, ~20% fewer instructions at d = 30).
 // KEEP_UPPER: leave whatever the elimination left above the diagonal instead of zeroing it on the way out (32 selects
 // + predicate packing per lane); for callers that only ever read the lower triangle (the substitutions).
-template <typename T, int D, bool PADDED = false, bool KEEP_UPPER = false>
-__device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n) {
+// FUSE_MV: the factor is not written back at all; lane i returns y_i = sum_{j <= i} L_ij x_j in *yreg instead (the
+// sampler needs L only to form L eps: saves the masked write-back, the reload and a shared-memory round trip).
+// dg / dginv may be null when the caller does not need them (dead stores and the sqrt product disappear).
+template <typename T, int D, bool PADDED = false, bool KEEP_UPPER = false, bool FUSE_MV = false>
+__device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n, const T* xvec = nullptr,
+                                         T* yreg = nullptr) {
   constexpr int LD = Tile<D>::LD;
   constexpr int V = (D >= 4) ? 4 : D;
   cta_sync<D>();
@@ -428,7 +432,7 @@ __device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n
         T* cb = colbuf + (k & 1) * D;
         if (lane < D) cb[lane] = lik;
         if (PADDED ? (lane == 0) : (lane == k)) {  // every lane holds the same pivot: PADDED lets lane 0 publish it
-          dg[k] = lkk;
+          if (dg) dg[k] = lkk;
           if (dginv) dginv[k] = inv;
         }
         __syncwarp();
@@ -450,7 +454,21 @@ __device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n
         }
       }
     }
-    if ((PADDED && lane < D) || lane < n) {
+    if constexpr (FUSE_MV) {
+      T a0 = T(0), a1 = T(0);
+#pragma unroll
+      for (int j = 0; j < D; j += V) {
+        T xv[V];
+        ldv<T, V>(xv, xvec + j);
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+          if (j + q <= lane) {
+            if (q & 1) a1 = fma_(row[j + q], xv[q], a1); else a0 = fma_(row[j + q], xv[q], a0);
+          }
+        }
+      }
+      *yreg = a0 + a1;
+    } else if ((PADDED && lane < D) || lane < n) {
 #pragma unroll
       for (int j = 0; j < D; j += V) {
         T tmp[V];
