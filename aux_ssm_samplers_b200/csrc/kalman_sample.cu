@@ -80,6 +80,77 @@ template <typename T, int D> __device__ __forceinline__ T chol_times_vec_pad(T* 
   return (bad || l >= n) ? T(0) : y;
 }
 
+// One warp, fp32, D = 32:  P <- P - Z^T Z  on the tensor cores with the 3xTF32 split (hi*hi + hi*lo + lo*hi, fp32
+// accumulate: error 5e-7 of max|P|, the same as the FFMA form; single-pass TF32 would be 2e-4 -- profiles/
+// r2_tf32x3_probe.jsonl).  Why here: the elements kernel is bound by SHARED-MEMORY bandwidth (ncu: 0.85 wavefronts per
+// clock per SM); the register-tiled FFMA2 product reads 12 words per lane per k (3 LDS.128 = 12 wavefronts), the MMA
+// fragments 8 words per lane per EIGHT k -- Z^T Z is symmetric in its operand, so the A fragment of m-tile i is made of
+// the B-fragment values of n-tiles 2i and 2i + 1 -- and only the 6 of 8 (16 x 8) output tiles that touch the lower
+// triangle are formed (the result feeds a Cholesky factorisation).
+__device__ __forceinline__ unsigned to_tf32(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <int LD> __device__ __forceinline__ void ztz_sub_3xtf32(const float* Z, float* P) {
+  __syncwarp();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float c[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[i][j][q] = 0.f;
+#pragma unroll
+  for (int k0 = 0; k0 < 32; k0 += 8) {
+    unsigned hi[4][2], lo[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float v = Z[(k0 + t + 4 * q) * LD + 8 * j + g];
+        hi[j][q] = to_tf32(v);
+        lo[j][q] = to_tf32(v - __uint_as_float(hi[j][q]));
+      }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      // a0:(m = 16 i + g, k = t)  a1:(m + 8, k = t)  a2:(m, k = t + 4)  a3:(m + 8, k = t + 4)
+      const unsigned ah[4] = {hi[2 * i][0], hi[2 * i + 1][0], hi[2 * i][1], hi[2 * i + 1][1]};
+      const unsigned al[4] = {lo[2 * i][0], lo[2 * i + 1][0], lo[2 * i][1], lo[2 * i + 1][1]};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (8 * j <= 16 * i + 15) {  // the tile touches the lower triangle
+          mma_tf32_16x8x8(c[i][j], al, hi[j]);
+          mma_tf32_16x8x8(c[i][j], ah, lo[j]);
+          mma_tf32_16x8x8(c[i][j], ah, hi[j]);
+        }
+      }
+    }
+  }
+  // c0:(row g, col 2t) c1:(row g, col 2t + 1) c2:(row g + 8, col 2t) c3:(row g + 8, col 2t + 1)
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (8 * j <= 16 * i + 15) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float2* pp = reinterpret_cast<float2*>(P + (16 * i + g + 8 * h) * LD + 8 * j + 2 * t);
+          float2 v = *pp;
+          v.x -= c[i][j][2 * h];
+          v.y -= c[i][j][2 * h + 1];
+          *pp = v;
+        }
+      }
+  __syncwarp();
+}
+
 // B <- L^{-T} B for the n x m block (thread j owns column j), right-looking: for i = n-1..0
 //   z_i = b_i / L_ii ;  b_k -= L_ik z_i  (k < i)      -- uses ROW i of L, i.e. broadcast vector loads.
 // dg = the workspace filled by the factorisation.  Register-resident for D <= 32.
@@ -390,7 +461,9 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
     // (a fused forward + backward substitution that keeps the column in registers and stores G^T straight to global
     // memory was measured: 11.06 ms per call instead of 10.34 -- 192 bytes of spills at the 128-register cap)
     fwd_solve<T, D, PAD>(s.S, s.Z, nullptr, dx, dx, s.dg);  // Zs = Ls^{-1} F P
-    mm_tn<T, D, 2>(s.Z, s.Z, s.P, s.P, PAD ? D : dx);       // Sigma = P - Zs^T Zs  (lower triangle feeds the Cholesky)
+    // Sigma = P - Zs^T Zs  (the lower triangle feeds the Cholesky)
+    if constexpr (PAD && D == 32 && sizeof(T) == 4) ztz_sub_3xtf32<LD>(reinterpret_cast<const float*>(s.Z), reinterpret_cast<float*>(s.P));
+    else mm_tn<T, D, 2>(s.Z, s.Z, s.P, s.P, PAD ? D : dx);
     bwd_solve<T, D, PAD>(s.S, s.Z, s.dg, dx, dx);           // Z <- G^T = Ls^{-T} Zs
     if (PAD && t + 1 < t_hi) pad_prefetch();                // chol(S) is dead: its buffer receives P_{t+1}
     if (BULK && bulk_ok && t + 1 < t_hi) bulk_stage(t + 1);  // chol(S) is dead: the TMA unit refills its buffer
