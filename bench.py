@@ -398,11 +398,26 @@ def kalman_leg(ctx, args, peaks, fp32_peak):
     peak_fp32 = float(fp32_peak.get("fp32_tflops", 72.0))
     traffic = load_json("profiles/traffic_r2.json", load_json("profiles/traffic_r1.json", {})).get("per_launch", {})
 
-    def ncu_traffic(label):
+    def ncu_entry(label):
         for k, v in traffic.items():
             if label.startswith(k.split("<")[0]):
-                return v["dram_read_bytes"] + v["dram_write_bytes"]
+                return v
         return None
+
+    def ncu_traffic(label):
+        v = ncu_entry(label)
+        return None if v is None else v["dram_read_bytes"] + v["dram_write_bytes"]
+
+    def ncu_smem(label):
+        """Shared-memory data-pipe load of the kernel from the committed ncu capture (not measurable with CUDA events):
+        the sampler elements kernel is bound by it, not by FP32 issue or HBM."""
+        v = ncu_entry(label)
+        if v is None or "lsu_wavefronts_pct_of_peak" not in v:
+            return None
+        return {"bound": "shared-memory data pipe (l1tex__data_pipe_lsu_wavefronts, 1 wavefront / clock / SM)",
+                "frac_of_peak": v["lsu_wavefronts_pct_of_peak"] / 100.0,
+                "shared_wavefronts_per_unit": v.get("shared_wavefronts", 0) / float(units_launch),
+                "source": "profiles/traffic_r2.json (ncu counters of the same kernel at the same shape)"}
 
     cands = {
         "auxssm_kalman_filter_f32": dict(
@@ -432,7 +447,7 @@ def kalman_leg(ctx, args, peaks, fp32_peak):
             "alg_flops_per_unit": cnd["flops_unit"], "units_per_launch": units_launch,
             "survey_flops_per_unit": cnd["survey_flops_unit"],
             "survey_achieved_tflops": cnd["survey_flops_unit"] * units_launch / (per * 1e-3) / 1e12,
-            "traffic": ncu_traffic(cnd["kernel"]),
+            "traffic": ncu_traffic(cnd["kernel"]), "smem": ncu_smem(cnd["kernel"]),
             "traffic_source": "profiles/traffic_r*.json (ncu --set full, dram__bytes_read + write of the call's dominant kernel)",
             "hbm": {"alg_bytes_per_unit": cnd["survey_bytes_unit"], "interface_bytes_per_unit": cnd["bytes_unit"],
                     "interface_achieved_gbs": cnd["bytes_unit"] * units_launch / (per * 1e-3) / 1e9,

@@ -8,7 +8,7 @@ OUT=gpurun_out
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu --skip-cfg5 --csmc-chains 592"
 $CMD > $OUT/r2_plain.json 2> $OUT/r2_plain.err || { echo "plain run failed"; tail -5 $OUT/r2_plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/r2_launches.csv $CMD > $OUT/r2_ncu_launch.log 2>&1
-METRICS="gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,launch__registers_per_thread,launch__grid_size,launch__block_size,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio,smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"
+METRICS="gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,launch__registers_per_thread,launch__grid_size,launch__block_size,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_tensor.sum,smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio,smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"
 i=0
 # kernel regex : launches of it to skip (the structured / general instantiations of the Kalman kernels alternate behind
 # the diagonal-F gate; a late launch is a warm one)
