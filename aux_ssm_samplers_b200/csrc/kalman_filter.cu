@@ -511,6 +511,7 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
   __shared__ __align__(16) T ev_[WPC][D];
   __shared__ __align__(16) T rdv_[WPC][D];
   __shared__ T svbuf_[WPC][D], mvec_[WPC][D];
+  __shared__ __align__(16) T zbuf_[WPC][4 * (D + 4)];  // Z = L_b^{-1} P[I, :] of the current block (see below)
   const int wq = threadIdx.x >> 5;
   T* stage = stage_[wq];
   T* rowbuf = stage_[wq];  // the row-exchange buffers alias the output stage (disjoint in time, __syncwarp between)
@@ -639,13 +640,18 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
             }
           }
           __syncwarp();
+          // EXCH: every lane used to run the 4 x 4 substitution twice, on its TM row entries and on its TN column
+          // entries of the same 4 x D matrix Z (P is symmetric).  With TM = 8 that was 2/3 of the substitution work and
+          // a quarter of the kernel's FMA-pipe time; now only the TN column entries are solved and the row entries are
+          // re-read from a 4 x D shared image of Z that the ty = 0 lanes publish.
+          constexpr bool EXCH = (TM % 2 == 0) && (TN % 2 == 0) && (TM > TN);
           T sr[NB][NB], rdl[NB], evl[NB], RA[NB][TM], RC[NB][TN], v[NB];
           ldv<T, NB>(rdl, rdv + i0);
           ldv<T, NB>(evl, ev + i0);
 #pragma unroll
           for (int aa = 0; aa < NB; ++aa) {
             ldv<T, NB>(sr[aa], rb + aa * RS + i0);
-            ldv<T, TM>(RA[aa], rb + aa * RS + ty * TM);
+            if (!EXCH) ldv<T, TM>(RA[aa], rb + aa * RS + ty * TM);
             ldv<T, TN>(RC[aa], rb + aa * RS + tx * TN);
             v[aa] = evl[aa] - rb[aa * RS + D];
           }
@@ -664,8 +670,10 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
                 const T okb = ((bits >> bb) & 1u) ? T(1) : T(0);
                 L[aa][bb] = (aa == bb) ? (oka != T(0) ? sr[aa][aa] + rdl[aa] : T(1)) : oka * okb * sr[aa][bb];
               }
+              if (!EXCH) {
 #pragma unroll
-              for (int r = 0; r < TM; ++r) RA[aa][r] *= oka;
+                for (int r = 0; r < TM; ++r) RA[aa][r] *= oka;
+              }
 #pragma unroll
               for (int cc = 0; cc < TN; ++cc) RC[aa][cc] *= oka;
               v[aa] *= oka;
@@ -705,7 +713,19 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
             Pair<T> x3 = pair_mul_s(inv[3], pair_fma_s(n32, x2, pair_fma_s(n31, x1, pair_fma_s(n30, x0, pair_make(a3, b3)))));
             pair_get(x0, a0, b0); pair_get(x1, a1, b1); pair_get(x2, a2, b2); pair_get(x3, a3, b3);
           };
-          if constexpr (TM % 2 == 0 && TN % 2 == 0) {
+          if constexpr (EXCH) {
+#pragma unroll
+            for (int cc = 0; cc < TN; cc += 2)
+              fsub2(RC[0][cc], RC[0][cc + 1], RC[1][cc], RC[1][cc + 1], RC[2][cc], RC[2][cc + 1], RC[3][cc], RC[3][cc + 1]);
+            T* zb = zbuf_[wq];
+            if (ty == 0) {
+#pragma unroll
+              for (int aa = 0; aa < NB; ++aa) stv<T, TN>(zb + aa * RS + tx * TN, RC[aa]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int aa = 0; aa < NB; ++aa) ldv<T, TM>(RA[aa], zb + aa * RS + ty * TM);
+          } else if constexpr (TM % 2 == 0 && TN % 2 == 0) {
 #pragma unroll
             for (int r = 0; r < TM; r += 2)
               fsub2(RA[0][r], RA[0][r + 1], RA[1][r], RA[1][r + 1], RA[2][r], RA[2][r + 1], RA[3][r], RA[3][r + 1]);
