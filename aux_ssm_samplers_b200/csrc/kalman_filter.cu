@@ -530,6 +530,11 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
   const T* Qg = a.Qs ? a.Qs + unit_off(a.d.Qs, c, b) : nullptr;
   const T* bg = a.bs ? a.bs + unit_off(a.d.bs, c, b) : nullptr;
   T p[TM][TN], q[TM][TN], mreg[TM], fa[TM], fc[TN], ba[TM];
+  // MROW (the blocked exchange path, see EXCH below): the filtered mean lives ONE ENTRY PER LANE (lane = row) and is
+  // updated from the shared image of Z with 4 FMAs per block; the register-tile form below it (every lane carrying the
+  // TM entries of its row group, only the tx = 0 copies ever read) cost 4 TM FMAs per block, 17 % of the block.
+  constexpr bool MROW = (TM % 4 == 0) && (TM % 2 == 0) && (TN % 2 == 0) && (TM > TN) && (D <= 32);
+  T m_own = T(0), f_own = T(0), b_own = T(0);
 #pragma unroll
   for (int cc = 0; cc < TN; ++cc) {
     const int cb = tx * TN + cc;
@@ -554,12 +559,17 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
 #pragma unroll
   for (int r = 0; r < TM; ++r) {
     const int ra = ty * TM + r;
-    mreg[r] = (tx == 0 && ra < d) ? m_src[ra] : T(0);
+    mreg[r] = (!MROW && tx == 0 && ra < d) ? m_src[ra] : T(0);
 #pragma unroll
     for (int cc = 0; cc < TN; ++cc) {
       const int cb = tx * TN + cc;
       p[r][cc] = (ra < d && cb < d) ? P_src[ra * d + cb] : T(0);
     }
+  }
+  if (MROW && lane < d) {
+    m_own = m_src[lane];
+    f_own = Fg ? Fg[lane * d + lane] : T(0);
+    b_own = bg ? bg[lane] : T(0);
   }
   const T* yg = a.ys + unit_off(a.d.ys, c, b);
   const T* rg = a.Rs + unit_off(a.d.Rs, c, b);
@@ -606,8 +616,9 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
 #pragma unroll
           for (int cc = 0; cc < TN; ++cc) p[r][cc] = fma_(fa[r] * fc[cc], p[r][cc], q[r][cc]);
         }
-        mreg[r] = fma_(fa[r], mreg[r], ba[r]);
+        if (!MROW) mreg[r] = fma_(fa[r], mreg[r], ba[r]);
       }
+      if (MROW) m_own = fma_(f_own, m_own, b_own);
     }
     __syncwarp();
     // ---- measurement update: blocks of four scalar observations ----
@@ -636,9 +647,10 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
 #pragma unroll
             for (int aa = 0; aa < NB; ++aa) {
               stv<T, TN>(rb + aa * RS + tx * TN, p[hb * NB + aa]);
-              if (tx == 0) rb[aa * RS + D] = mreg[hb * NB + aa];
+              if (!MROW && tx == 0) rb[aa * RS + D] = mreg[hb * NB + aa];
             }
           }
+          if (MROW && lane >= i0 && lane < i0 + NB) rb[(lane - i0) * RS + D] = m_own;
           __syncwarp();
           // EXCH: every lane used to run the 4 x 4 substitution twice, on its TM row entries and on its TN column
           // entries of the same 4 x D matrix Z (P is symmetric).  With TM = 8 that was 2/3 of the substitution work and
@@ -752,8 +764,9 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
                   const Pair<T> pp = pair_fma_s(RA[aa][r], nrc[c2], pair_make(p[r][2 * c2], p[r][2 * c2 + 1]));
                   pair_get(pp, p[r][2 * c2], p[r][2 * c2 + 1]);
                 }
-                mreg[r] = fma_(RA[aa][r], v[aa], mreg[r]);  // only the tx == 0 copies are ever read
+                if (!MROW) mreg[r] = fma_(RA[aa][r], v[aa], mreg[r]);  // only the tx == 0 copies are ever read
               }
+              if (MROW) m_own = fma_(zbuf_[wq][aa * RS + lane], v[aa], m_own);  // m_row += Z[aa][row] v[aa]
             } else {
 #pragma unroll
               for (int r = 0; r < TM; ++r) {
@@ -815,8 +828,9 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
 #pragma unroll
     for (int r = 0; r < TM; ++r) {
       stv<T, TN>(stage + (ty * TM + r) * LDS_ + tx * TN, p[r]);
-      if (tx == 0) mvec[ty * TM + r] = mreg[r];
+      if (!MROW && tx == 0) mvec[ty * TM + r] = mreg[r];
     }
+    if (MROW && lane < D) mvec[lane] = m_own;
     __syncwarp();
     if (!want_out) continue;
     T* Pt = Psg + (int64_t)t * a.d.Ps.time;
