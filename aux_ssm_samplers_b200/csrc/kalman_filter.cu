@@ -766,7 +766,7 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
                 }
                 if (!MROW) mreg[r] = fma_(RA[aa][r], v[aa], mreg[r]);  // only the tx == 0 copies are ever read
               }
-              if (MROW) m_own = fma_(zbuf_[wq][aa * RS + lane], v[aa], m_own);  // m_row += Z[aa][row] v[aa]
+              if (MROW) m_own = fma_(zbuf_[wq][aa * RS + (lane < D ? lane : 0)], v[aa], m_own);  // m_row += Z[aa][row] v[aa]
             } else {
 #pragma unroll
               for (int r = 0; r < TM; ++r) {

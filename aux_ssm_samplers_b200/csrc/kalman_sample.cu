@@ -97,35 +97,41 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-template <int LD> __device__ __forceinline__ void ztz_sub_3xtf32(const float* Z, float* P) {
-  __syncwarp();
+// One warp's share: the two 16-row m-tiles M0, M1 against all D / 8 n-tiles (those touching the lower triangle only).
+template <int D, int LD, int M0, int M1> __device__ __forceinline__ void ztz_sub_tiles(const float* Z, float* P) {
+  constexpr int NTI = D / 8;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  float c[2][4][4];
+  float c[2][NTI][4];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NTI; ++j)
 #pragma unroll
       for (int q = 0; q < 4; ++q) c[i][j][q] = 0.f;
+  constexpr int MT[2] = {M0, M1};
+  constexpr int JMAX = (16 * (M0 > M1 ? M0 : M1) + 15) / 8;  // last n-tile any of the two m-tiles needs
 #pragma unroll
-  for (int k0 = 0; k0 < 32; k0 += 8) {
-    unsigned hi[4][2], lo[4][2];
+  for (int k0 = 0; k0 < D; k0 += 8) {
+    unsigned hi[NTI][2], lo[NTI][2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NTI; ++j) {
+      if (j <= JMAX) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const float v = Z[(k0 + t + 4 * q) * LD + 8 * j + g];
-        hi[j][q] = to_tf32(v);
-        lo[j][q] = to_tf32(v - __uint_as_float(hi[j][q]));
+        for (int q = 0; q < 2; ++q) {
+          const float v = Z[(k0 + t + 4 * q) * LD + 8 * j + g];
+          hi[j][q] = to_tf32(v);
+          lo[j][q] = to_tf32(v - __uint_as_float(hi[j][q]));
+        }
       }
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      // a0:(m = 16 i + g, k = t)  a1:(m + 8, k = t)  a2:(m, k = t + 4)  a3:(m + 8, k = t + 4)
-      const unsigned ah[4] = {hi[2 * i][0], hi[2 * i + 1][0], hi[2 * i][1], hi[2 * i + 1][1]};
-      const unsigned al[4] = {lo[2 * i][0], lo[2 * i + 1][0], lo[2 * i][1], lo[2 * i + 1][1]};
+      // a0:(m = 16 M + g, k = t)  a1:(m + 8, k = t)  a2:(m, k = t + 4)  a3:(m + 8, k = t + 4): the B values of n-tiles 2M, 2M+1
+      const unsigned ah[4] = {hi[2 * MT[i]][0], hi[2 * MT[i] + 1][0], hi[2 * MT[i]][1], hi[2 * MT[i] + 1][1]};
+      const unsigned al[4] = {lo[2 * MT[i]][0], lo[2 * MT[i] + 1][0], lo[2 * MT[i]][1], lo[2 * MT[i] + 1][1]};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (8 * j <= 16 * i + 15) {  // the tile touches the lower triangle
+      for (int j = 0; j < NTI; ++j) {
+        if (8 * j <= 16 * MT[i] + 15) {  // the tile touches the lower triangle
           mma_tf32_16x8x8(c[i][j], al, hi[j]);
           mma_tf32_16x8x8(c[i][j], ah, lo[j]);
           mma_tf32_16x8x8(c[i][j], ah, hi[j]);
@@ -137,18 +143,29 @@ template <int LD> __device__ __forceinline__ void ztz_sub_3xtf32(const float* Z,
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (8 * j <= 16 * i + 15) {
+    for (int j = 0; j < NTI; ++j)
+      if (8 * j <= 16 * MT[i] + 15) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          float2* pp = reinterpret_cast<float2*>(P + (16 * i + g + 8 * h) * LD + 8 * j + 2 * t);
+          float2* pp = reinterpret_cast<float2*>(P + (16 * MT[i] + g + 8 * h) * LD + 8 * j + 2 * t);
           float2 v = *pp;
           v.x -= c[i][j][2 * h];
           v.y -= c[i][j][2 * h + 1];
           *pp = v;
         }
       }
-  __syncwarp();
+}
+// D = 32: one warp, m-tiles {0, 1}.  D = 64: two warps; the lower triangle gives m-tile M (16 rows) 2M + 2 n-tiles of
+// work, so the pairs {0, 3} and {1, 2} balance the two warps (10 tiles each).
+template <int D, int LD> __device__ __forceinline__ void ztz_sub_3xtf32(const float* Z, float* P) {
+  cta_sync<D>();
+  if constexpr (D == 32) {
+    ztz_sub_tiles<32, LD, 0, 1>(Z, P);
+  } else {
+    static_assert(D == 64, "tensor-core product: D = 32 or 64");
+    if ((threadIdx.x >> 5) == 0) ztz_sub_tiles<64, LD, 0, 3>(Z, P); else ztz_sub_tiles<64, LD, 1, 2>(Z, P);
+  }
+  cta_sync<D>();
 }
 
 // B <- L^{-T} B for the n x m block (thread j owns column j), right-looking: for i = n-1..0
@@ -462,7 +479,8 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
     // memory was measured: 11.06 ms per call instead of 10.34 -- 192 bytes of spills at the 128-register cap)
     fwd_solve<T, D, PAD>(s.S, s.Z, nullptr, dx, dx, s.dg);  // Zs = Ls^{-1} F P
     // Sigma = P - Zs^T Zs  (the lower triangle feeds the Cholesky)
-    if constexpr (PAD && D == 32 && sizeof(T) == 4) ztz_sub_3xtf32<LD>(reinterpret_cast<const float*>(s.Z), reinterpret_cast<float*>(s.P));
+    if constexpr (LEAN && (D == 32 || D == 64) && sizeof(T) == 4)
+      ztz_sub_3xtf32<D, LD>(reinterpret_cast<const float*>(s.Z), reinterpret_cast<float*>(s.P));
     else mm_tn<T, D, 2>(s.Z, s.Z, s.P, s.P, PAD ? D : dx);
     bwd_solve<T, D, PAD>(s.S, s.Z, s.dg, dx, dx);           // Z <- G^T = Ls^{-T} Zs
     if (PAD && t + 1 < t_hi) pad_prefetch();                // chol(S) is dead: its buffer receives P_{t+1}
