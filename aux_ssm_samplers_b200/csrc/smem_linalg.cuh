@@ -746,10 +746,74 @@ __device__ __forceinline__ void chol_reg64(T* A, T* dg, T* dginv, T* colbuf, int
   cta_sync<64>();
 }
 
+// Two-warp Cholesky for D = 64: thread r (of the item's 64) owns row r in registers and BOTH warps work on every column
+// (the one-warp chol_reg64 left the item's second warp at a barrier for ~29 % of the d = 64 sampler's time).  One named
+// barrier per column: the RAW column k (a_rk, pivot included) is exchanged through a double-buffered shared vector, every
+// thread derives 1/l_kk from a_kk itself, and the update is written row[c] -= (a_rk / a_kk) a_ck, i.e. one scalar
+// s_r = a_rk inv^2 per thread and one FMA per element against the raw column -- no second exchange of the scaled column.
+// FAST: bare MUFU.RSQ pivots (fp32 structured paths, see pivot_fast_).
+template <typename T, bool FAST = false>
+__device__ __forceinline__ void chol_rows64(T* A, T* dg, T* dginv, T* colbuf, int n) {
+  constexpr int D = 64, LD = Tile<D>::LD, V = 4;
+  cta_sync<64>();
+  const int r = threadIdx.x;
+  T row[D];
+#pragma unroll
+  for (int j = 0; j < D; j += V) {
+    T tmp[V];
+    ldv<T, V>(tmp, A + r * LD + j);
+#pragma unroll
+    for (int q = 0; q < V; ++q) row[j + q] = (r < n) ? tmp[q] : T(0);
+  }
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    if (k < n) {  // uniform over the item
+      T* cb = colbuf + (k & 1) * D;
+      cb[r] = row[k];
+      cta_sync<64>();
+      const T akk = cb[k];
+      T lkk, inv;
+      if constexpr (FAST) pivot_fast_<T>(akk, lkk, inv); else pivot_<T>(akk, lkk, inv);
+      const T lrk = (r == k) ? lkk : row[k] * inv;
+      row[k] = lrk;
+      if (r == 0) {
+        dg[k] = lkk;
+        if (dginv) dginv[k] = inv;
+      }
+      const T ns = -(lrk * inv);
+#pragma unroll
+      for (int j = ((k + 1) / V) * V; j < D; j += V) {
+        T c[V];
+        ldv<T, V>(c, cb + j);
+#pragma unroll
+        for (int q = 0; q < V; q += 2) {
+          if (j + q > k) {
+            const Pair<T> r2 = pair_fma_s(ns, pair_make(c[q], c[q + 1]), pair_make(row[j + q], row[j + q + 1]));
+            pair_get(r2, row[j + q], row[j + q + 1]);
+          } else if (j + q + 1 > k) {
+            row[j + q + 1] = fma_(ns, c[q + 1], row[j + q + 1]);
+          }
+        }
+      }
+    }
+  }
+  if (r < n) {
+#pragma unroll
+    for (int j = 0; j < D; j += V) {
+      T tmp[V];
+#pragma unroll
+      for (int q = 0; q < V; ++q) tmp[q] = (j + q <= r) ? row[j + q] : T(0);
+      stv<T, V>(A + r * LD + j, tmp);
+    }
+  }
+  cta_sync<64>();
+}
+
 // In-place lower Cholesky of the n x n block; strict upper triangle zeroed; non-PD pivots give NaN.
 template <typename T, int D, bool PADDED = false, bool KEEP_UPPER = false>
 __device__ __forceinline__ void chol_inplace(T* A, T* dg, int n) {
   if constexpr (D <= 32) chol_reg<T, D, PADDED, KEEP_UPPER>(A, dg, dg + D, dg + 2 * D, n);
+  else if constexpr (D == 64 && Tile<D>::NT == 64) chol_rows64<T, false>(A, dg, dg + D, dg + 2 * D, n);
   else if constexpr (D == 64 && Tile<D>::NT >= 32) chol_reg64<T, PADDED>(A, dg, dg + D, dg + 2 * D, n);
   else chol_generic<T, D>(A, dg, n);
 }
