@@ -429,6 +429,10 @@ __device__ __forceinline__ void chol_reg(T* A, T* dg, T* dginv, T* colbuf, int n
         // PADDED (fast pivot): l_kk = a_kk * inv is what row[k] * inv gives on lane k itself, no select needed
         const T lik = PADDED ? row[k] * inv : ((lane == k) ? lkk : row[k] * inv);
         row[k] = lik;
+        // Column exchange through the double-buffered shared vector.  (Exchanging it with 31 - k shuffles per column
+        // instead was measured -- profiles/micro/shfl_vs_lds_probe.cu: SHFL and LDS share a pipe, 0.42 vs 0.68 clocks
+        // per broadcast word -- but the sampler call went 10.2 -> 11.5 ms: four times the instructions on the serial
+        // path of every column.)
         T* cb = colbuf + (k & 1) * D;
         if (lane < D) cb[lane] = lik;
         if (PADDED ? (lane == 0) : (lane == k)) {  // every lane holds the same pivot: PADDED lets lane 0 publish it
