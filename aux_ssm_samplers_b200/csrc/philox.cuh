@@ -41,11 +41,15 @@ static __device__ __noinline__ void philox_block(int mode, uint64_t seed, uint64
   if (mode == PHILOX_UNIFORM) {
     v[0] = a0; v[1] = a1; v[2] = a2; v[3] = a3;
   } else {
-    const float r0 = sqrtf(-2.0f * logf(a0)), r1 = sqrtf(-2.0f * logf(a2));
-    float s0, c0, s1, c1;
-    sincospif(2.0f * a1, &s0, &c0);
-    sincospif(2.0f * a3, &s1, &c1);
-    v[0] = r0 * c0; v[1] = r0 * s0; v[2] = r1 * c1; v[3] = r1 * s1;
+    // fp32 Box-Muller on the special-function unit: MUFU.LG2 / RSQ / SIN / COS (absolute errors ~2^-21, i.e. the
+    // fp32 rounding level of the result) instead of the ~20-instruction libm paths of logf / sincospif: in the
+    // cSMC sweeps with in-kernel draws the generator was about half of the instructions.  The angle is folded into
+    // [-pi, pi), where MUFU.SIN / COS are most accurate.  a0 <= 1 - 2^-25, so t > 0.
+    const float t0 = -2.0f * __logf(a0), t1 = -2.0f * __logf(a2);
+    const float r0 = t0 * rsqrtf(t0), r1 = t1 * rsqrtf(t1);
+    const float w0 = 6.283185307179586f * (a1 - (a1 >= 0.5f ? 1.0f : 0.0f));
+    const float w1 = 6.283185307179586f * (a3 - (a3 >= 0.5f ? 1.0f : 0.0f));
+    v[0] = r0 * __cosf(w0); v[1] = r0 * __sinf(w0); v[2] = r1 * __cosf(w1); v[3] = r1 * __sinf(w1);
   }
 }
 static __device__ __noinline__ void philox_block(int mode, uint64_t seed, uint64_t call, uint64_t blk, double (&v)[2]) {
