@@ -345,13 +345,21 @@ def mh_accept(x, x_prop, u, delta, log_lgssm_prop, log_lgssm_rev, log_target_pro
 # --------------------------------------------------------------------------------------------
 
 def get_kernel(dynamics_factory, observations_factory, log_likelihood_fn, parallel, *, time_chunks=0,
-               f_diagonal=False):
+               f_diagonal=False, prior_cancels=False):
     """Auxiliary Kalman sampler: returns ``(init, kernel)`` exactly like the reference
     (kalman/generic.py:19-95; note the reference's docstring lists them the other way round).
 
     ``dynamics_factory(x) -> (m0, P0, Fs, Qs, bs)``, ``observations_factory(x, u, delta) -> (ys, Hs, Rs, cs)``
     and ``log_likelihood_fn(x) -> [C]`` operate on CUDA tensors with a leading chain axis.
     ``kernel(key, state, delta) -> KalmanSampler``; ``state.x`` is ``[C, T, d]`` or ``[T, d]``.
+
+    ``prior_cancels=True`` is for adapters whose target is "the proposal's own dynamics x a potential" (the SV and
+    latent-Gaussian models): the acceptance ratio of generic.py:98-106 contains ``log p(x)`` under the dynamics once
+    inside ``log_target`` and once, with the opposite sign, inside ``posterior_logpdf`` -- for the proposal and for the
+    reverse move -- so the four evaluations cancel analytically.  With the flag the proposal densities are evaluated
+    as ``log p(y | x) - ell`` (base.py:138-166 minus ``ell``) and ``log_likelihood_fn`` must return the target WITHOUT
+    its ``log p(x)`` term; the acceptance probability is the same up to the rounding of the cancelled terms (|log p(x)|
+    is ~1e4 here, so dropping them makes ``alpha`` more, not less, accurate in fp32).  Default: the reference's form.
     """
 
     def do_one(sampling_key, u, delta, x, x_prop=None):
@@ -364,7 +372,10 @@ def get_kernel(dynamics_factory, observations_factory, log_likelihood_fn, parall
         if x_prop is None:
             x_prop = sampling(sampling_key, ms, Ps, lgssm, parallel, time_chunks=time_chunks,
                               f_diagonal=f_diagonal)
-        log_lgssm = posterior_logpdf(ys, x_prop, ell, lgssm, f_diagonal=f_diagonal)
+        if prior_cancels:
+            log_lgssm = _logpdf(_lib.LOGPDF_LOGLIK | _lib.LOGPDF_MINUS_ELL, ys, x_prop, ell, lgssm, False, f_diagonal)
+        else:
+            log_lgssm = posterior_logpdf(ys, x_prop, ell, lgssm, f_diagonal=f_diagonal)
         return log_lgssm, log_likelihood_fn(x_prop), x_prop
 
     def kernel(key, state, delta):

@@ -65,8 +65,13 @@ def log_potential(ys, x, out=None):
     return out
 
 
-def get_kernel(ys, m0, P0, F, Q, b, parallel, order=1, *, time_chunks=0, dense_R=False):
-    """auxiliary_kalman.py:10-57: auxiliary Kalman sampler for the SV model, first or second order."""
+def get_kernel(ys, m0, P0, F, Q, b, parallel, order=1, *, time_chunks=0, dense_R=False, prior_cancels=True):
+    """auxiliary_kalman.py:10-57: auxiliary Kalman sampler for the SV model, first or second order.
+
+    The SV target is the proposal's own latent dynamics times the observation potential, so the ``log p(x)`` terms of
+    the acceptance ratio cancel (``kalman.get_kernel(prior_cancels=True)``): by default neither the two
+    ``prior_logpdf`` calls of ``log_likelihood_fn`` (:50-54) nor the prior part of the two ``posterior_logpdf`` calls are
+    evaluated.  ``prior_cancels=False`` evaluates all four like the reference does."""
     d = m0.shape[0]
     # the SV dynamics are F = phi I (model.py:35-43): hint the structured kernels.  The hint is verified on the device
     # on every call (include/auxssm.h), so a dense F passed here still gives the general kernels' results.
@@ -82,8 +87,10 @@ def get_kernel(ys, m0, P0, F, Q, b, parallel, order=1, *, time_chunks=0, dense_R
     prior_lgssm = kalman.LGSSM(m0, P0, Fs, Qs, bs, None, None, None)
 
     def log_likelihood_fn(x):
+        if prior_cancels:
+            return log_potential(ys, x)
         out = kalman.prior_logpdf(x, prior_lgssm)  # mvn.logpdf(x0; m0, P0) + sum_t mvn.logpdf(x_t; F x_{t-1} + b, Q)
         return log_potential(ys, x, out=out)
 
     return kalman.get_kernel(dynamics_factory, obs_factory, log_likelihood_fn, parallel, time_chunks=time_chunks,
-                             f_diagonal=f_diagonal)
+                             f_diagonal=f_diagonal, prior_cancels=prior_cancels)
