@@ -168,6 +168,29 @@ template <int D, int LD> __device__ __forceinline__ void ztz_sub_3xtf32(const fl
   cta_sync<D>();
 }
 
+// D = 64 lean path (two warps, ONE item per CTA): y_r = (chol(A) x)_r with NaN -> 0, the factor never stored.
+template <typename T> __device__ __forceinline__ T chol_times_vec64(T* A, T* dg, const T* x, int n) {
+  T y = T(0);
+  chol_rows64<T, sizeof(T) == 4, true>(A, dg, nullptr, dg + 2 * 64, n, x, &y);
+  const int l = threadIdx.x;
+  const bool mine = (l < n) && (!(dg[l < n ? l : 0] > T(0)) || !finite_(dg[l < n ? l : 0]));
+  const bool bad = __syncthreads_or(mine ? 1 : 0) != 0;  // W = 1: the item's 64 threads are the whole CTA
+  return (bad || l >= n) ? T(0) : y;
+}
+
+// global [dx x dx] <- shared [dx x LD] for a multi-warp item: 16-byte chunks (dx % 4 == 0, 16-byte aligned g)
+template <typename T, int D> __device__ __forceinline__ void store_chunks(T* __restrict__ g, const T* s, int dx) {
+  constexpr int LD = Tile<D>::LD, NT = Tile<D>::NT;
+  const int cpr = dx / 4;
+#pragma unroll 4
+  for (int ch = threadIdx.x; ch < dx * cpr; ch += NT) {
+    const int r = ch / cpr, c4 = (ch - r * cpr) * 4;
+    T v[4];
+    ldv<T, 4>(v, s + r * LD + c4);
+    stv<T, 4>(g + r * dx + c4, v);
+  }
+}
+
 // B <- L^{-T} B for the n x m block (thread j owns column j), right-looking: for i = n-1..0
 //   z_i = b_i / L_ii ;  b_k -= L_ik z_i  (k < i)      -- uses ROW i of L, i.e. broadcast vector loads.
 // dg = the workspace filled by the factorisation.  Register-resident for D <= 32.
@@ -438,6 +461,9 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
         const T le = chol_times_vec_pad<T, D>(s.P, s.dg, s.eps, dx);
         g = reinterpret_cast<T*>(ctx[3]);
         if (i < dx) g[dx * dx + i] = s.m[i] + le;
+      } else if constexpr (BULK) {
+        const T le = chol_times_vec64<T>(s.P, s.dg, s.eps, dx);
+        if (i < dx) g[dx * dx + i] = s.m[i] + le;
       } else {
         chol_nan_to_zero<T, D, PAD>(s.P, s.dg, dx);
         mv_nn<T, D, 1>(s.P, s.eps, s.e, s.m, dx, dx);
@@ -500,6 +526,7 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
       }
     }
     if constexpr (PAD) chol_reg<T, D, true, true>(s.S, nullptr, s.dg + D, s.dg + 2 * D, dx);  // lower triangle + 1/diag only
+    else if constexpr (BULK) chol_rows64<T, sizeof(T) == 4>(s.S, s.dg, s.dg + D, s.dg + 2 * D, dx);
     else chol_inplace<T, D, PAD>(s.S, s.dg, dx);
     // (a fused forward + backward substitution that keeps the column in registers and stores G^T straight to global
     // memory was measured: 11.06 ms per call instead of 10.34 -- 192 bytes of spills at the 128-register cap)
@@ -513,17 +540,24 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
     if (BULK && bulk_ok && t + 1 < t_hi) bulk_stage(t + 1);  // chol(S) is dead: the TMA unit refills its buffer
     T l_eps = T(0);
     if constexpr (PAD) l_eps = chol_times_vec_pad<T, D>(s.P, s.dg, s.eps, dx);  // L eps, L = chol(Sigma) (NaN -> 0)
+    else if constexpr (BULK) l_eps = chol_times_vec64<T>(s.P, s.dg, s.eps, dx);
     else chol_nan_to_zero<T, D, PAD>(s.P, s.dg, dx);        // L = chol(Sigma), NaN -> 0
     if (PAD) {
       mv_tn_pad<T, D, 2>(s.Z, s.r, s.e, s.m);               // e = m - G (F m + b)     (G v = (G^T)^T v)
       if (i < D) s.e[i] += l_eps;                           // e += L eps
+      cta_sync<D>();
+    } else if (BULK) {
+      mv_tn<T, D, 2>(s.Z, s.r, s.e, s.m, dx, dx);
+      if (i < dx) s.e[i] += l_eps;
       cta_sync<D>();
     } else {
       mv_tn<T, D, 2>(s.Z, s.r, s.e, s.m, dx, dx);
       mv_nn<T, D, 1>(s.P, s.eps, s.e, s.e, dx, dx);
     }
     if (PAD) g = reinterpret_cast<T*>(ctx[3]);
-    if (PAD && pairs_ok) store_rows_pairs<T, D>(g, s.Z, dx); else store_mat<T, D>(g, s.Z, dx, dx);
+    if (PAD && pairs_ok) store_rows_pairs<T, D>(g, s.Z, dx);
+    else if (BULK && (dx % 4) == 0 && (reinterpret_cast<uintptr_t>(g) % (4 * sizeof(T))) == 0) store_chunks<T, D>(g, s.Z, dx);
+    else store_mat<T, D>(g, s.Z, dx, dx);
     if (i < dx) g[dx * dx + i] = s.e[i];
     if (PAD) {
       __syncwarp();

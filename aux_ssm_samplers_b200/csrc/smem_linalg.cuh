@@ -756,8 +756,10 @@ __device__ __forceinline__ void chol_reg64(T* A, T* dg, T* dginv, T* colbuf, int
 // thread derives 1/l_kk from a_kk itself, and the update is written row[c] -= (a_rk / a_kk) a_ck, i.e. one scalar
 // s_r = a_rk inv^2 per thread and one FMA per element against the raw column -- no second exchange of the scaled column.
 // FAST: bare MUFU.RSQ pivots (fp32 structured paths, see pivot_fast_).
-template <typename T, bool FAST = false>
-__device__ __forceinline__ void chol_rows64(T* A, T* dg, T* dginv, T* colbuf, int n) {
+// FUSE_MV: the factor is not written back; thread r returns y_r = sum_{j <= r} L_rj x_j in *yreg (see chol_reg).
+template <typename T, bool FAST = false, bool FUSE_MV = false>
+__device__ __forceinline__ void chol_rows64(T* A, T* dg, T* dginv, T* colbuf, int n, const T* xvec = nullptr,
+                                            T* yreg = nullptr) {
   constexpr int D = 64, LD = Tile<D>::LD, V = 4;
   cta_sync<64>();
   const int r = threadIdx.x;
@@ -801,7 +803,21 @@ __device__ __forceinline__ void chol_rows64(T* A, T* dg, T* dginv, T* colbuf, in
       }
     }
   }
-  if (r < n) {
+  if constexpr (FUSE_MV) {
+    T a0 = T(0), a1 = T(0);
+#pragma unroll
+    for (int j = 0; j < D; j += V) {
+      T xv[V];
+      ldv<T, V>(xv, xvec + j);
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        if (j + q <= r) {
+          if (q & 1) a1 = fma_(row[j + q], xv[q], a1); else a0 = fma_(row[j + q], xv[q], a0);
+        }
+      }
+    }
+    *yreg = a0 + a1;
+  } else if (r < n) {
 #pragma unroll
     for (int j = 0; j < D; j += V) {
       T tmp[V];
