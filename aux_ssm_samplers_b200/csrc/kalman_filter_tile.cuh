@@ -205,6 +205,9 @@ __global__ void __launch_bounds__(128, 2) filter_tile_kernel(FilterArgs<T> a, in
           Pair<T> x3 = pair_mul_s(inv[3], pair_fma_s(n32, x2, pair_fma_s(n31, x1, pair_fma_s(n30, x0, pair_make(a3, b3)))));
           pair_get(x0, a0, b0); pair_get(x1, a1, b1); pair_get(x2, a2, b2); pair_get(x3, a3, b3);
         };
+        // (Solving Z once and exchanging its column entries through shared memory, as filter_warp_kernel does, was
+        // measured here too: 41.3 instead of 39.2 ms per call -- the second 128-thread barrier per block costs more than
+        // the saved substitutions.)
 #pragma unroll
         for (int r = 0; r < TM; r += 2)
           fsub2(RA[0][r], RA[0][r + 1], RA[1][r], RA[1][r + 1], RA[2][r], RA[2][r + 1], RA[3][r], RA[3][r + 1]);
