@@ -363,7 +363,11 @@ def _aux_u(key, x, delta):
     """u = x + sqrt(delta_t / 2) eps with per-time-step delta (csmc/generic.py:61-67)."""
     from .kalman import auxiliary_draw
     C, T, d = x.shape
-    dl = torch.as_tensor(delta, dtype=x.dtype, device=x.device)
+    if torch.is_tensor(delta):
+        dl = torch.as_tensor(delta, dtype=x.dtype, device=x.device)
+    else:
+        from .kalman import _as_delta
+        dl = _as_delta(delta, 1, x.dtype, x.device)[0]  # cached device scalar: no blocking host copy per sweep
     dl = dl.expand(T) if dl.dim() == 0 else dl
     shared = dl.dim() == 1
     dl2 = dl.expand(C, T) if shared else dl
