@@ -44,8 +44,11 @@ static __device__ __noinline__ void philox_block(int mode, uint64_t seed, uint64
     // fp32 Box-Muller on the special-function unit: MUFU.LG2 / RSQ / SIN / COS (absolute errors ~2^-21, i.e. the
     // fp32 rounding level of the result) instead of the ~20-instruction libm paths of logf / sincospif: in the
     // cSMC sweeps with in-kernel draws the generator was about half of the instructions.  The angle is folded into
-    // [-pi, pi), where MUFU.SIN / COS are most accurate.  a0 <= 1 - 2^-25, so t > 0.
-    const float t0 = -2.0f * __logf(a0), t1 = -2.0f * __logf(a2);
+    // [-pi, pi), where MUFU.SIN / COS are most accurate.  ((word >> 8) + 0.5) rounds to 2^24 in fp32 when the 24 bits
+    // are all ones (one uniform in 2^24 is exactly 1.0f): then -2 log a = -0.0, rsqrt(-0.0) = -inf and the radius
+    // -0 * -inf = NaN -- a NaN normal every ~1.7e7 pairs (it froze 32 of the 8192 configs[4] chains at their
+    // initial state).  The clamp makes that radius ~0, which is what sqrt(-2 log 1) is; all other draws keep their bits.
+    const float t0 = fmaxf(-2.0f * __logf(a0), 1e-30f), t1 = fmaxf(-2.0f * __logf(a2), 1e-30f);
     const float r0 = t0 * rsqrtf(t0), r1 = t1 * rsqrtf(t1);
     const float w0 = 6.283185307179586f * (a1 - (a1 >= 0.5f ? 1.0f : 0.0f));
     const float w1 = 6.283185307179586f * (a3 - (a3 >= 0.5f ? 1.0f : 0.0f));
