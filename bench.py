@@ -790,6 +790,12 @@ def run_gpu(args):
             "accept_rate_last_step": k["accept_rate"], "all_finite": k["finite"], "diagnostics": diag,
             "csmc": csmc_legs, "config5": cfg5, "few_chain": few, "pit_csmc": pit,
         }
+        # a leg whose states went non-finite is not a measurement: say so loudly (stderr + a key in the line)
+        legs = [("headline", line)] + [(l["config"], l) for l in csmc_legs] + [("configs[4]", cfg5), ("pit_csmc", pit)]
+        bad = [name for name, l in legs if l is not None and l.get("all_finite") is False]
+        line["non_finite_legs"] = bad
+        if bad:
+            print("bench.py: NON-FINITE STATES in %s -- those numbers are invalid" % bad, file=sys.stderr, flush=True)
         if ctx.world == 1 and not args.no_cpu:
             cores = len(os.sched_getaffinity(0))
             v, ms, sample = cpu_kalman(1, 0, chains_per_worker=16, workers=cores)

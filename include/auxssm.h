@@ -352,7 +352,8 @@ int32_t auxssm_kalman_sweep_f64(void* stream, const auxssm_sweep_desc* desc, con
  * mcmc_stats       running statistics of the outer loop, examples/stochastic_volatility/experiment.py:98-127:
  *                  stats[c] = {n, acceptance mean, windowed acceptance (EMA with weight beta), mean squared jump};
  *                  `updated` is int32 [n_chains, per_step].
- * philox           counter-based Philox4x32-10 uniforms in (0,1) / Box-Muller normals (stand-in for jax.random):
+ * philox           counter-based Philox4x32-10 uniforms in (0,1) (fp32: (0,1] -- ((w >> 8) + 0.5) / 2^24 rounds to 1.0f
+ *                  when the 24 bits are all ones; consumers clamp) / Box-Muller normals, always finite (stand-in for jax.random):
  *                  element stream = f(seed, *counter); *counter (device memory, may be NULL = 0) is incremented by
  *                  one after the fill, so a captured CUDA graph draws fresh numbers on every replay.  Restated bit
  *                  for bit (uniforms) in oracle/philox.py.                                                        */
