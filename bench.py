@@ -212,6 +212,37 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def bind_near_gpu(index):
+    """Pin this process to the CPUs of the GPU's own NUMA node BEFORE any pinned host buffer exists, so that the
+    end-to-end arm's staging buffers are allocated (first touch) on the node the GPU's PCIe root hangs off.  Eight ranks
+    each move 252 MB per step through host memory; with every buffer on one socket they contend for it and for the
+    inter-socket link.  Best effort: any failure leaves the affinity as it was."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s" % (dom[-4:].lower(), rest.lower())
+        node = int(open(path + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(path + "/local_cpulist").read().strip().split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        info.update({"pci": bus, "numa_node": node, "local_cpus": len(cpus), "allowed_local_cpus": len(allowed)})
+        if node >= 0 and len(allowed) >= 2:
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+    except Exception as exc:  # noqa: BLE001
+        info["error"] = repr(exc)[:120]
+    return info
+
+
 class Ctx:
     """Per-process distributed / device context and timing helpers."""
 
@@ -225,6 +256,8 @@ class Ctx:
         assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
         torch.cuda.set_device(self.local)
         self.device = torch.device("cuda", self.local)
+        self.orig_affinity = os.sched_getaffinity(0)
+        self.numa = bind_near_gpu(self.local)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.device)
 
@@ -785,7 +818,7 @@ def run_gpu(args):
                              "126 MB each); no flush needed",
                        "draws": "`value`: externally supplied normals / uniforms resident in HBM (parity mode), 2 rotating "
                                 "sets; `e2e`: generated on the device (Philox)"},
-            "clocks": k["clock_info"], "e2e": k["e2e"], "gpu_launches": k["launches"], "kernels": k["kernels_seen"],
+            "clocks": k["clock_info"], "host_numa": ctx.numa, "e2e": k["e2e"], "gpu_launches": k["launches"], "kernels": k["kernels_seen"],
             "roofline": k["roofline"], "roofline_other": k["roofline_other"], "kernel_ms": k["kernel_ms"],
             "accept_rate_last_step": k["accept_rate"], "all_finite": k["finite"], "diagnostics": diag,
             "csmc": csmc_legs, "config5": cfg5, "few_chain": few, "pit_csmc": pit,
@@ -797,6 +830,7 @@ def run_gpu(args):
         if bad:
             print("bench.py: NON-FINITE STATES in %s -- those numbers are invalid" % bad, file=sys.stderr, flush=True)
         if ctx.world == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, ctx.orig_affinity)  # the CPU baseline uses every core the box gives us
             cores = len(os.sched_getaffinity(0))
             v, ms, sample = cpu_kalman(1, 0, chains_per_worker=16, workers=cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
