@@ -278,6 +278,19 @@ def test_logpdf_fast_path_time_invariant(dtype, d, T, C):
                         ok.log_likelihood(ys, xs, full), rtol=r)
     npt.assert_allclose(host(kalman.posterior_logpdf(dev(ys, dtype), dev(xs, dtype), dev(ell, dtype), glg)),
                         ok.posterior_logpdf(ys, xs, ell, full), rtol=r)
+    # likelihood-only call with a time-invariant offset c (stride 0) and an infinite variance entry (dropped from the
+    # dimension count, mvn/base.py:49-57; -inf through norm.logpdf when d = 1, kalman/base.py:160-162): the
+    # row-per-warp kernel
+    c0 = rng.standard_normal(d)
+    rdiag2 = rdiag.copy()
+    rdiag2[C - 1, 2, d - 1] = np.inf
+    Rd = np.zeros((C, T, d, d))
+    Rd[..., np.arange(d), np.arange(d)] = rdiag2  # (inf * eye would put NaN off the diagonal)
+    full_c = full[:6] + (Rd, np.broadcast_to(c0, (T, d)))
+    glg_c = glg._replace(Rs=kalman.Diagonal(dev(rdiag2, dtype)), cs=dev(c0[None, None], dtype))
+    with np.errstate(all="ignore"):
+        want = ok.log_likelihood(ys, xs, full_c)
+    npt.assert_allclose(host(kalman.log_likelihood(dev(ys, dtype), dev(xs, dtype), glg_c)), want, rtol=r)
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
