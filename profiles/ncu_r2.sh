@@ -12,7 +12,7 @@ METRICS="gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.p
 i=0
 # kernel regex : launches of it to skip (the structured / general instantiations of the Kalman kernels alternate behind
 # the diagonal-F gate; a late launch is a warm one)
-for SPEC in "sample_elements_kernel:4" "filter_warp_kernel:4" "sample_replay_kernel:2" "logpdf_fast_kernel:4" "csmc_multi_kernel:1" "csmc_wide_kernel:1" "kalman_sweep_fused_kernel:2" "pit_stitch_kernel:12"; do
+for SPEC in "sample_elements_kernel:4" "filter_warp_kernel:4" "sample_replay_kernel:2" "loglik_rows_kernel:4" "csmc_multi_kernel:1" "csmc_wide_kernel:1" "kalman_sweep_fused_kernel:2" "pit_stitch_kernel:12"; do
   K=${SPEC%%:*}; S=${SPEC##*:}
   i=$((i+1))
   ncu --metrics $METRICS --clock-control none --kernel-name-base demangled -k regex:"$K" -s $S -c 1 --csv --log-file $OUT/r2_full_$i.csv $CMD > $OUT/r2_ncu_full_$i.log 2>&1
@@ -22,7 +22,7 @@ import csv, glob, json
 out = {}
 for f in sorted(glob.glob("$OUT/r2_full_*.csv")):
     rows = [r for r in csv.reader(open(f)) if len(r) > 10]
-    if len(rows) < 2:
+    if len(rows) < 2 or "Kernel Name" not in rows[0]:
         continue
     h = rows[0]
     name = rows[1][h.index("Kernel Name")]

@@ -24,7 +24,7 @@ lines = ["ncu launch list of `python bench.py --steps 1 --warmup 3 --no-cpu --sk
          "%-60s %8s %12s %7s" % ("kernel", "launches", "total ms", "share")]
 for k, v in tot.most_common(30):
     lines.append("%-60s %8d %12.3f %6.1f%%" % (k[:60], cnt[k], v / 1e6, 100 * v / T))
-kal = [k for k in tot if any(s in k for s in ('filter_warp', 'sample_elements', 'sample_replay', 'logpdf', 'sv_', 'auxiliary_draw',
+kal = [k for k in tot if any(s in k for s in ('filter_warp', 'sample_elements', 'sample_replay', 'logpdf', 'loglik_rows', 'sv_', 'auxiliary_draw',
                                               'kalman_mh', 'count_offdiag', 'ell_reduce'))]
 Tk = sum(tot[k] for k in kal)
 lines += ["", "Kernels of the headline aux-Kalman sweep only (share of their summed time, ms per launch):"]
