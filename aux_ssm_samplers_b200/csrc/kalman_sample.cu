@@ -568,8 +568,9 @@ sample_elements_kernel(SampleArgs<T> a, int n_tiles) {
 
 // pass 2: x_{T-1} = e_{T-1};  x_t = G_t x_{t+1} + e_t.  One CTA per unit (one warp for D <= 32, two for D = 64), thread i
 // owns x_t[i] and column i of G_t^T (coalesced over i).  The loop is strictly sequential and streams (d^2 + d) s bytes per
-// step, so its speed is the number of bytes in flight (Little's law): the columns of the NEXT TWO steps are requested
-// into registers before the product of step t is formed (one step ahead gave 3.3 TB/s = 51 % of the HBM peak).
+// step, so its speed is the number of bytes in flight (Little's law): the columns of the next steps are requested
+// into registers before the product of step t is formed (one step ahead gave 3.3 TB/s = 51 % of the HBM peak, two
+// 4.3 TB/s; D <= 32 now keeps three in flight).
 template <typename T, int D> struct ReplayCfg { static constexpr int NT = (D <= 32) ? 32 : 64; };
 
 template <typename T, int D>
@@ -591,9 +592,6 @@ __global__ void __launch_bounds__(ReplayCfg<T, D>::NT) sample_replay_kernel(Samp
     xb[0][i] = x;
     xo[(int64_t)(Tn - 1) * a.d.xs.time + i] = x;
   }
-  T g1[D], g2[D], e1 = T(0), e2 = T(0);  // steps t - 1 and t - 2 in flight
-#pragma unroll
-  for (int k = 0; k < D; ++k) { g1[k] = T(0); g2[k] = T(0); }
   auto fetch = [&](int tt, T (&gn)[D], T& en) {
     if (tt >= 0 && act) {
       const T* g = base + (int64_t)tt * ssz;  // G^T (row k, column i) then e
@@ -602,11 +600,59 @@ __global__ void __launch_bounds__(ReplayCfg<T, D>::NT) sample_replay_kernel(Samp
       en = g[dx * dx + i];
     }
   };
+  constexpr int V = (D >= 4) ? 4 : D;
+  if constexpr (D <= 32) {
+    // One warp: a ring of NB register buffers, the time loop unrolled NB-fold so that buffer s always serves steps
+    // t0 - s, t0 - s - NB, ... (no register rotation); a buffer is refilled for NB steps later as soon as its
+    // multiply-adds have been issued, which keeps NB - 1 steps (3 x 3.7 KB per warp at d = 30) in flight during a
+    // product instead of two.  Same accumulation order as before: bit-identical draws.
+    constexpr int NB = 4;
+    T g[NB][D], e[NB];
+#pragma unroll
+    for (int s = 0; s < NB; ++s) {
+      e[s] = T(0);
+#pragma unroll
+      for (int k = 0; k < D; ++k) g[s][k] = T(0);
+    }
+#pragma unroll
+    for (int s = 0; s < NB; ++s) fetch(Tn - 2 - s, g[s], e[s]);
+    sync();
+    int cur = 0;
+    for (int t0 = Tn - 2; t0 >= 0; t0 -= NB) {
+#pragma unroll
+      for (int s = 0; s < NB; ++s) {
+        const int t = t0 - s;
+        if (t >= 0) {  // warp-uniform
+          T acc0 = e[s], acc1 = T(0);
+#pragma unroll
+          for (int k = 0; k < D; k += V) {
+            T xv[V];
+            ldv<T, V>(xv, &xb[cur][k]);
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+              if (q & 1) acc1 = fma_(g[s][k + q], xv[q], acc1); else acc0 = fma_(g[s][k + q], xv[q], acc0);
+            }
+          }
+          fetch(t - NB, g[s], e[s]);
+          x = acc0 + acc1;
+          if (act) {
+            xb[cur ^ 1][i] = x;
+            xo[(int64_t)t * a.d.xs.time + i] = x;
+          }
+          sync();
+          cur ^= 1;
+        }
+      }
+    }
+    return;
+  }
+  T g1[D], g2[D], e1 = T(0), e2 = T(0);  // D = 64 (two warps): steps t - 1 and t - 2 in flight
+#pragma unroll
+  for (int k = 0; k < D; ++k) { g1[k] = T(0); g2[k] = T(0); }
   fetch(Tn - 2, g1, e1);
   fetch(Tn - 3, g2, e2);
   sync();
   int cur = 0;
-  constexpr int V = (D >= 4) ? 4 : D;
   for (int t = Tn - 2; t >= 0; --t) {
     T gc[D];
 #pragma unroll
