@@ -323,6 +323,9 @@ def _as_delta(delta, C, dtype, dev):
         # of a scalar step size is made once by an asynchronous fill and reused.
         key = (float(delta), dtype, dev)
         dl = _DELTA_CACHE.get(key)
+        if dl is None and torch.cuda.is_current_stream_capturing():
+            # inside a CUDA-graph capture the fill belongs to the graph (and its memory to the graph's pool): not cached
+            return torch.full((1,), float(delta), dtype=dtype, device=dev)
         if dl is None:
             if len(_DELTA_CACHE) >= 256:
                 _DELTA_CACHE.clear()
