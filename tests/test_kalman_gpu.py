@@ -257,7 +257,8 @@ def test_filter_and_logpdf_diagonal_R(dtype, d, T, C, dense_h, chunks, fkind):
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("d,T,C", [(1, 5, 2), (4, 300, 3), (30, 130, 2), (64, 140, 2)])
 def test_logpdf_fast_path_time_invariant(dtype, d, T, C):
-    """Time-invariant (stride-0) dynamics + H = I + diagonal R take the thread-per-time-step kernel."""
+    """Time-invariant (stride-0) dynamics + H = I + diagonal R take the thread-per-time-step kernel (prior / posterior)
+    and the row-per-warp kernel (likelihood alone)."""
     from aux_ssm_samplers_b200 import kalman
     rng = np.random.default_rng(100 + d)
     _, lg = random_lgssm(rng, T, d, d, stable=True)
