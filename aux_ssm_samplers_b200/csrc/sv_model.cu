@@ -10,6 +10,7 @@
 //                             [.., d, d] exactly like the reference materialises it)
 //   auxiliary_kalman.py:50-54 the potential part of log_likelihood_fn (sum of g over t and dims).
 #include "common.cuh"
+#include "smem_linalg.cuh"  // ldv / stv (vector accesses)
 
 namespace auxssm {
 
@@ -25,29 +26,45 @@ template <> __device__ __forceinline__ double nan_to_num_<double>(double v) {
   return v;
 }
 
-// One thread per (chain, t, dim) entry for ys'; the dense R_t block of an entry's (chain, t) is written
-// cooperatively by the threads of that block row (second order only).
+// One element of ys' (and of the diagonal of Omega_t, second order).
 template <typename T>
-__global__ void sv_obs_factory_kernel(int order, int64_t n_chains, int64_t Tn, int d, const T* __restrict__ ys,
+__device__ __forceinline__ void sv_obs_elem(int order, T dl, T y, T xv, T uv, T& aux, T& omega) {
+  const T w = T(0.5) * y * y * exp(-xv);  // y^2 e^{-x} / 2
+  const T grad = w - T(0.5);
+  const T hess = -w;
+  if (order == 1) {
+    aux = uv + T(0.5) * dl * nan_to_num_(grad);
+    omega = T(0);
+  } else {
+    omega = T(1) / (-hess + T(2) / dl);
+    aux = omega * (T(2) * uv / dl + grad - hess * xv);
+  }
+}
+
+// ys' (and diag R_t): blockIdx.y walks the chains, a thread owns VEC consecutive (t, dim) entries of one chain -- no
+// 64-bit division per entry, 16-byte accesses when the chain length and the bases allow (VEC = 4); the dense R_t
+// block of the reference layout is written by sv_second_order_R_kernel.
+template <typename T, int VEC>
+__global__ void sv_obs_factory_kernel(int order, int64_t n_chains, int64_t per, const T* __restrict__ ys,
                                       int64_t ys_chain_stride, const T* __restrict__ x, const T* __restrict__ u,
                                       const T* __restrict__ delta, int delta_stride, T* __restrict__ aux_ys,
                                       T* __restrict__ Rdiag) {
-  const int64_t total = n_chains * Tn * d;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = e / (Tn * d);
-    const int64_t td = e - c * Tn * d;  // t * d + i
+  for (int64_t c = blockIdx.y; c < n_chains; c += gridDim.y) {
     const T dl = delta[c * delta_stride];
-    const T y = ys[c * ys_chain_stride + td];
-    const T xv = x[e], uv = u[e];
-    const T w = T(0.5) * y * y * exp(-xv);  // y^2 e^{-x} / 2
-    const T grad = w - T(0.5);
-    const T hess = -w;
-    if (order == 1) {
-      aux_ys[e] = uv + T(0.5) * dl * nan_to_num_(grad);
-    } else {
-      const T omega = T(1) / (-hess + T(2) / dl);
-      aux_ys[e] = omega * (T(2) * uv / dl + grad - hess * xv);
-      if (Rdiag) Rdiag[e] = omega;  // diagonal layout: R[c, t, i]
+    const T* yc = ys + c * ys_chain_stride;
+    const T *xc = x + c * per, *uc = u + c * per;
+    T* ac = aux_ys + c * per;
+    T* rc = Rdiag ? Rdiag + c * per : nullptr;
+    for (int64_t td = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; td < per;
+         td += (int64_t)gridDim.x * blockDim.x * VEC) {
+      T yv[VEC], xv[VEC], uv[VEC], av[VEC], ov[VEC];
+      ldv<T, VEC>(yv, yc + td);
+      ldv<T, VEC>(xv, xc + td);
+      ldv<T, VEC>(uv, uc + td);
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) sv_obs_elem<T>(order, dl, yv[q], xv[q], uv[q], av[q], ov[q]);
+      stv<T, VEC>(ac + td, av);
+      if (order == 2 && rc) stv<T, VEC>(rc + td, ov);  // diagonal layout: R[c, t, i]
     }
   }
 }
@@ -118,13 +135,22 @@ static int sv_factory_entry(void* stream, int32_t order, int64_t n_chains, int64
     return AUXSSM_ERR_INVALID;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t total = n_chains * Tn * d;
-  int64_t blocks = (total + 255) / 256;
+  const int64_t per = Tn * d, total = n_chains * per;
   const int64_t cap = 32L * device_sm_count();
-  if (blocks > cap) blocks = cap;
-  sv_obs_factory_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(order, n_chains, Tn, d, ys, ys_chain_stride, x, u, delta,
-                                                              delta_stride, aux_ys,
-                                                              (order == 2 && !dense_R) ? Rs : nullptr);
+  T* rdiag = (order == 2 && !dense_R) ? Rs : nullptr;
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  const bool vec4 = per % 4 == 0 && ys_chain_stride % 4 == 0 && al16(ys) && al16(x) && al16(u) && al16(aux_ys) &&
+                    (rdiag == nullptr || al16(rdiag));
+  const unsigned gy = (unsigned)(n_chains < 65535 ? n_chains : 65535);
+  if (vec4) {
+    const unsigned gx = (unsigned)((per / 4 + 255) / 256);
+    sv_obs_factory_kernel<T, 4><<<dim3(gx, gy), 256, 0, st>>>(order, n_chains, per, ys, ys_chain_stride, x, u, delta,
+                                                              delta_stride, aux_ys, rdiag);
+  } else {
+    const unsigned gx = (unsigned)((per + 255) / 256);
+    sv_obs_factory_kernel<T, 1><<<dim3(gx, gy), 256, 0, st>>>(order, n_chains, per, ys, ys_chain_stride, x, u, delta,
+                                                              delta_stride, aux_ys, rdiag);
+  }
   AUXSSM_CHECK_LAUNCH("auxssm_sv_obs_factory");
   if (order == 1) {
     const int64_t tot = n_chains * (dense_R ? (int64_t)d * d : d);
