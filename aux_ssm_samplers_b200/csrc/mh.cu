@@ -7,6 +7,7 @@
 // One CTA per chain for the accept step (block reduction over the T*d trajectory entries, fixed
 // order => deterministic), grid-stride vectorised loop for the auxiliary draw.
 #include "common.cuh"
+#include "smem_linalg.cuh"  // ldv / stv (vector accesses)
 
 namespace auxssm {
 
@@ -19,6 +20,27 @@ __global__ void auxiliary_draw_kernel(int64_t n_chains, int64_t n_per_chain, con
     const int64_t c = e / n_per_chain;
     const T s = sqrt(T(0.5) * delta[c * delta_stride]);
     u[e] = x[e] + s * normals[e];
+  }
+}
+
+// Long chains (the aux-Kalman sweep: n_per_chain = T d): blockIdx.y walks the chains, so the scale is computed once per
+// thread instead of a 64-bit division and a square root per entry, and a thread moves VEC consecutive entries.
+template <typename T, int VEC>
+__global__ void auxiliary_draw_rows_kernel(int64_t n_chains, int64_t n_per_chain, const T* __restrict__ x,
+                                           const T* __restrict__ normals, const T* __restrict__ delta,
+                                           int delta_stride, T* __restrict__ u) {
+  for (int64_t c = blockIdx.y; c < n_chains; c += gridDim.y) {
+    const T s = sqrt(T(0.5) * delta[c * delta_stride]);
+    const int64_t base = c * n_per_chain;
+    for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; e < n_per_chain;
+         e += (int64_t)gridDim.x * blockDim.x * VEC) {
+      T xv[VEC], nv[VEC], uv[VEC];
+      ldv<T, VEC>(xv, x + base + e);
+      ldv<T, VEC>(nv, normals + base + e);
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) uv[q] = xv[q] + s * nv[q];
+      stv<T, VEC>(u + base + e, uv);
+    }
   }
 }
 
@@ -67,6 +89,14 @@ static int aux_draw_entry(void* stream, int64_t n_chains, int64_t n_per_chain, c
   if (!x || !normals || !delta || !u || n_chains < 1 || n_per_chain < 1 || (delta_stride != 0 && delta_stride != 1)) {
     set_error("auxssm_auxiliary_draw: invalid argument");
     return AUXSSM_ERR_INVALID;
+  }
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  if (n_per_chain >= 4096 && n_per_chain % 4 == 0 && al16(x) && al16(normals) && al16(u)) {
+    const unsigned gx = (unsigned)((n_per_chain / 4 + 255) / 256), gy = (unsigned)(n_chains < 65535 ? n_chains : 65535);
+    auxiliary_draw_rows_kernel<T, 4><<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        n_chains, n_per_chain, x, normals, delta, delta_stride, u);
+    AUXSSM_CHECK_LAUNCH("auxssm_auxiliary_draw");
+    return AUXSSM_OK;
   }
   const int64_t total = n_chains * n_per_chain;
   int64_t blocks = (total + 255) / 256;
