@@ -824,7 +824,28 @@ filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
     // ---- outputs: tile -> shared -> coalesced rows ----
     // ell-only call (ms == Ps == NULL: the reverse proposal of kalman/generic.py:67 needs the likelihood only):
     // nothing is staged or stored, except the chunk-0 state a later chunk starts from.
-    if (!want_out && !(t + 1 == t1 && j == 0 && j + 1 < a.n_chunks)) continue;
+    const bool need_stage = (t + 1 == t1 && j == 0 && j + 1 < a.n_chunks);  // the state a later chunk starts from
+    if (!want_out && !need_stage) continue;
+    if constexpr (MROW && TN == 4) {
+      // Direct stores from the register tile: a lane's four columns of a row are 16 contiguous bytes of the compact
+      // row-major P_t (8-byte aligned when d is even), so the tile needs no trip through shared memory -- 8 STS.128 +
+      // 8 LDS.128 (64 shared-memory wavefronts) and two warp barriers fewer per step, the same 16 STG.64 per lane.
+      if (want_out && pairs_ok && !need_stage) {
+        T* Pt = Psg + (int64_t)t * a.d.Ps.time;
+        const int c0 = tx * TN;
+#pragma unroll
+        for (int r = 0; r < TM; ++r) {
+          const int row = ty * TM + r;
+          if (row < d) {
+            const T va[2] = {p[r][0], p[r][1]}, vb[2] = {p[r][2], p[r][3]};
+            if (c0 < d) stv<T, 2>(Pt + row * d + c0, va);
+            if (c0 + 2 < d) stv<T, 2>(Pt + row * d + c0 + 2, vb);
+          }
+        }
+        if (lane < d) msg[(int64_t)t * a.d.ms.time + lane] = m_own;
+        continue;
+      }
+    }
 #pragma unroll
     for (int r = 0; r < TM; ++r) {
       stv<T, TN>(stage + (ty * TM + r) * LDS_ + tx * TN, p[r]);
