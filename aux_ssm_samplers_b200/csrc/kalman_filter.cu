@@ -500,7 +500,8 @@ __global__ void __launch_bounds__(Tile<D>::NT, Occ<T, D>::MINB) filter_recursion
 // element, the measurement update is d rank-one updates (see run_recursion_scalar) with row i exchanged
 // through a double-buffered shared vector and __syncwarp only (no block barrier anywhere).  y_{t+1} and
 // diag(R_{t+1}) are prefetched into registers one step ahead so DRAM latency never sits on the critical
-// path; P_t / m_t are staged through shared memory and written with row-contiguous (coalesced) stores.
+// path; P_t / m_t are stored straight from the register tile (a lane's four columns of a row are 16 contiguous bytes of
+// the compact row-major P_t); only odd d / unaligned bases and the chunk hand-over go through the shared-memory stage.
 template <typename T, int D>
 __global__ void __launch_bounds__(128, 2)
 filter_warp_kernel(FilterArgs<T> a, int chunk_first) {
